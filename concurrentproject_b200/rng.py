@@ -1,0 +1,80 @@
+"""Portable counter-based sequence generator.
+
+The same function exists in C (oracle/gotoh_oracle.c: oracle_mix64 / oracle_random_acgt) and in
+CUDA (csrc/swb200_gen.cuh); all three are bit-identical, so the GPU path, the oracle and the
+fixtures see the same bytes.  This replaces the reference harness's unseeded
+``rand() % 4`` (TestFileWithGPU.cpp:25-36) and its libstdc++-specific
+``mt19937_64 + uniform_int_distribution`` (cudaSmithM.cu:200-213).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_NT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def mix64(seed: int, stream: int, index) -> np.ndarray:
+    """splitmix64-style finaliser of (seed, stream, index); index may be an array."""
+    idx = np.asarray(index, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+             + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+             + np.uint64((0xD1B54A32D192ED03 * (stream & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def random_codes(seed: int, stream: int, length: int) -> np.ndarray:
+    """length symbols in {0,1,2,3}: word k//32 of the stream, bits 2*(k%32)."""
+    if length <= 0:
+        return np.zeros(0, dtype=np.uint8)
+    nwords = (length + 31) // 32
+    words = mix64(seed, stream, np.arange(nwords, dtype=np.uint64))
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    codes = ((words[:, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(-1)
+    return codes[:length]
+
+
+def random_acgt(seed: int, stream: int, length: int) -> np.ndarray:
+    """ASCII bytes over {A,C,G,T}, identical to oracle_random_acgt(seed, stream, length)."""
+    return _NT[random_codes(seed, stream, length)]
+
+
+def mutate(seq: np.ndarray, seed: int, stream: int, sub_rate: float, indel_rate: float) -> np.ndarray:
+    """A copy of ``seq`` with i.i.d. substitutions and single-base insertions/deletions.
+
+    Used for planted-similarity pairs (cfg4 reads, cfg5 long reads).  Decisions come from
+    mix64(seed, stream, position) so the result is reproducible from (seed, stream) alone.
+    """
+    n = len(seq)
+    if n == 0:
+        return seq.copy()
+    r = mix64(seed, stream, np.arange(n, dtype=np.uint64))
+    u = (r >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+    newc = ((r >> np.uint64(3)) & np.uint64(3)).astype(np.uint8)
+    out = []
+    sub_hi = sub_rate
+    del_hi = sub_hi + indel_rate / 2.0
+    ins_hi = del_hi + indel_rate / 2.0
+    kind = np.zeros(n, dtype=np.uint8)          # 0 keep, 1 substitute, 2 delete, 3 insert-after
+    kind[u < ins_hi] = 3
+    kind[u < del_hi] = 2
+    kind[u < sub_hi] = 1
+    sub = _NT[newc]
+    # make substitutions real changes
+    same = (kind == 1) & (sub == seq)
+    sub = np.where(same, _NT[(newc + 1) & 3], sub)
+    keep = kind != 2
+    base = np.where(kind == 1, sub, seq)
+    # build with insertions
+    counts = np.where(keep, 1, 0) + np.where(kind == 3, 1, 0)
+    total = int(counts.sum())
+    res = np.empty(total, dtype=np.uint8)
+    pos = np.cumsum(counts) - counts
+    res[pos[keep]] = base[keep]
+    ins = kind == 3
+    res[pos[ins] + 1] = _NT[(newc[ins] + 2) & 3]
+    return res
