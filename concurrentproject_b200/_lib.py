@@ -1,0 +1,84 @@
+"""ctypes binding of concurrentproject_b200/lib/libswb200.so (C ABI: include/swb200.h, include/algoGPU.h).
+
+There is deliberately no fallback: if the CUDA library is missing or cannot be loaded, importing the
+API fails loudly.  Nothing in this package computes a score on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libswb200.so"
+
+
+class Params(C.Structure):
+    """swb200_params: MATCH / MISMATCH / G_INIT / G_EXT of the reference (main.cpp:20-23) as data."""
+    _fields_ = [("match", C.c_int), ("mismatch", C.c_int), ("gap_init", C.c_int), ("gap_ext", C.c_int)]
+
+
+class Options(C.Structure):
+    _fields_ = [("lanes", C.c_int), ("rows", C.c_int), ("config", C.c_int), ("ctas", C.c_int),
+                ("no_linear", C.c_int), ("reserved", C.c_int * 3)]
+
+
+class RunInfo(C.Structure):
+    _fields_ = [("lanes", C.c_int), ("linear", C.c_int), ("rows", C.c_int), ("config", C.c_int),
+                ("ctas", C.c_int), ("warps", C.c_int), ("bands", C.c_int), ("engine_launches", C.c_int),
+                ("aux_launches", C.c_int), ("cells", C.c_longlong), ("engine_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+ERRORS = {-1: "CUDA", -2: "ARG", -3: "ALPHABET", -4: "TIMEOUT", -5: "NOMEM", -6: "RANGE"}
+
+U8P = C.POINTER(C.c_ubyte)
+
+# every symbol include/swb200.h and include/algoGPU.h declare
+EXPORTS = {
+    "swb200_last_error": ([], C.c_char_p),
+    "swb200_device_count": ([], C.c_int),
+    "swb200_score": ([U8P, C.c_int, U8P, C.c_int, C.POINTER(Params), C.POINTER(C.c_int)], C.c_int),
+    "swb200_score_ex": ([U8P, C.c_longlong, U8P, C.c_longlong, C.POINTER(Params), C.POINTER(Options),
+                         C.POINTER(C.c_int)], C.c_int),
+    "swb200_ctx_create": ([C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "swb200_ctx_destroy": ([C.c_void_p], None),
+    "swb200_score_device": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(Params),
+                             C.POINTER(Options), C.c_void_p, C.POINTER(C.c_int)], C.c_int),
+    "swb200_last_run": ([C.c_void_p, C.POINTER(RunInfo)], C.c_int),
+    "SequentialSmithWatermanScoreGPU": ([U8P, U8P, C.c_int, C.c_int], C.c_int),
+    "SmithWatermanLazyGPU": ([U8P, U8P, C.c_int, C.c_int], C.c_int),
+    "SmithWatermanScoreCUDA": ([U8P, U8P, C.c_int, C.c_int], C.c_int),
+    "SmithDiagonalGPU": ([U8P, U8P, C.c_int, C.c_int], C.c_int),
+}
+
+_lib = None
+
+
+def build(jobs: int = 8) -> None:
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", f"-j{jobs}", "-C", str(PKG / "csrc")], check=True)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C concurrentproject_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (argtypes, restype) in EXPORTS.items():
+            fn = getattr(lib, name)      # AttributeError here = ABI drift, fail loudly
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+    return _lib
+
+
+class SwbError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        msg = load().swb200_last_error().decode(errors="replace")
+        super().__init__(f"{where}: SWB200_ERR_{ERRORS.get(code, code)}: {msg}")
+        self.code = code

@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference's score-function interface, on top of the C ABI.
+
+Same names, argument order and meaning as the reference headers: algoGPU.h:5-9
+(``SequentialSmithWatermanScoreGPU``, ``SmithWatermanLazyGPU``, ``SmithWatermanScoreCUDA``: two byte
+sequences and their lengths in, the int local-alignment score out) and
+SmithDiagonalGPUrefactored.cu:174 (``SmithDiagonalGPU``).  ``score`` adds what the reference keeps
+as per-file constants (main.cpp:20-23; README.md:46): MATCH / MISMATCH / GAP_INIT / GAP_EXT.
+Everything runs on the GPU through libswb200.so; there is no CPU path here."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import Options, Params, RunInfo, SwbError
+
+Bytes = Union[bytes, bytearray, str, np.ndarray]
+DEFAULT_PARAMS = (1, -1, 1, 1)  # MATCH, MISMATCH, GAP_INIT, GAP_EXT (main.cpp:20-23)
+
+
+def _u8(seq: Bytes) -> np.ndarray:
+    if isinstance(seq, str):
+        seq = seq.encode("latin1")
+    if isinstance(seq, (bytes, bytearray)):
+        return np.frombuffer(bytes(seq), dtype=np.uint8)
+    return np.ascontiguousarray(seq, dtype=np.uint8)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_lib.U8P)
+
+
+def _params(p) -> Params:
+    m, x, gi, ge = p
+    return Params(int(m), int(x), int(gi), int(ge))
+
+
+def _options(lanes=0, rows=0, config=0, ctas=0, no_linear=False) -> Options:
+    o = Options()
+    o.lanes, o.rows, o.config, o.ctas, o.no_linear = lanes, rows, config, ctas, int(bool(no_linear))
+    return o
+
+
+def _legacy(name: str, seq1: Bytes, seq2: Bytes, n: Optional[int], m: Optional[int]) -> int:
+    a, b = _u8(seq1), _u8(seq2)
+    n = len(a) if n is None else n
+    m = len(b) if m is None else m
+    if n > len(a) or m > len(b):
+        raise ValueError("length argument exceeds the buffer")
+    return int(getattr(_lib.load(), name)(_ptr(a), _ptr(b), n, m))
+
+
+def SequentialSmithWatermanScoreGPU(seq1: Bytes, seq2: Bytes, len1: Optional[int] = None, len2: Optional[int] = None) -> int:
+    """algoGPU.h:5 / simpleGPU.cu:109."""
+    return _legacy("SequentialSmithWatermanScoreGPU", seq1, seq2, len1, len2)
+
+
+def SmithWatermanLazyGPU(seq1: Bytes, seq2: Bytes, n: Optional[int] = None, m: Optional[int] = None) -> int:
+    """algoGPU.h:7 / cudaLazy.cu:58."""
+    return _legacy("SmithWatermanLazyGPU", seq1, seq2, n, m)
+
+
+def SmithWatermanScoreCUDA(seq1: Bytes, seq2: Bytes, n: Optional[int] = None, m: Optional[int] = None) -> int:
+    """algoGPU.h:9 / cudaSmithM.cu:128."""
+    return _legacy("SmithWatermanScoreCUDA", seq1, seq2, n, m)
+
+
+def SmithDiagonalGPU(seq1: Bytes, seq2: Bytes, n: Optional[int] = None, m: Optional[int] = None) -> int:
+    """SmithDiagonalGPUrefactored.cu:174."""
+    return _legacy("SmithDiagonalGPU", seq1, seq2, n, m)
+
+
+def score(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0, rows: int = 0,
+          config: int = 0, ctas: int = 0, no_linear: bool = False) -> int:
+    """Gotoh local-alignment score of two HOST byte sequences with runtime parameters (swb200_score_ex)."""
+    a, b = _u8(seq1), _u8(seq2)
+    out = C.c_int(0)
+    p, o = _params(params), _options(lanes, rows, config, ctas, no_linear)
+    rc = _lib.load().swb200_score_ex(_ptr(a), len(a), _ptr(b), len(b), C.byref(p), C.byref(o), C.byref(out))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_ex")
+    return out.value
+
+
+def last_run(ctx: Optional["Context"] = None) -> dict:
+    info = RunInfo()
+    rc = _lib.load().swb200_last_run(ctx.handle if ctx else None, C.byref(info))
+    if rc != 0:
+        raise SwbError(rc, "swb200_last_run")
+    return info.as_dict()
+
+
+class Context:
+    """A per-device engine context for sequences that already live in HBM (swb200_ctx_*)."""
+
+    def __init__(self, device: int = 0):
+        self.handle = C.c_void_p()
+        rc = _lib.load().swb200_ctx_create(device, C.byref(self.handle))
+        if rc != 0:
+            raise SwbError(rc, "swb200_ctx_create")
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            _lib.load().swb200_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score_device(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *,
+                     stream: int = 0, lanes: int = 0, rows: int = 0, config: int = 0, ctas: int = 0,
+                     no_linear: bool = False) -> int:
+        """d_seq1/d_seq2: device addresses of raw bytes (e.g. torch_tensor.data_ptr()); stream: cudaStream_t."""
+        out = C.c_int(0)
+        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear)
+        rc = _lib.load().swb200_score_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
+                                             C.byref(o), C.c_void_p(stream), C.byref(out))
+        if rc != 0:
+            raise SwbError(rc, "swb200_score_device")
+        return out.value
+
+    def last_run(self) -> dict:
+        return last_run(self)

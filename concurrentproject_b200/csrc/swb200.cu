@@ -1,0 +1,501 @@
+// swb200.cu -- C ABI of libswb200.so (see include/swb200.h, include/algoGPU.h).
+//
+// Host side of the hot path: what the reference's host functions do around their kernels
+// (simpleGPU.cu:109-163, cudaLazy.cu:58-99, cudaSmithM.cu:128-189: cudaMalloc x5, H2D x2, 2N-1
+// launches, D2H of the whole H matrix, host max, cudaFree x5) becomes: persistent context, two
+// H2D copies, two encode kernels, ONE cooperative launch of the wavefront engine, a 16-byte D2H.
+// There is no CPU fallback: every score comes from the engine kernels or the call fails.
+#include "../../include/swb200.h"
+#include "../../include/algoGPU.h"
+#include "swb_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define SWB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(SWB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+//  encode kernels: raw bytes -> 2-bit codes
+// ---------------------------------------------------------------------------------------------
+// Fast path: A,C,G,T -> (c >> 1) & 3 = 0,1,3,2 (injective on ACGT; equality scoring only needs an
+// injective recoding).  Any other byte sets STATUS_BAD_SYMBOL and the host re-encodes through a
+// 256-entry table built from the symbols actually present (covers the reference's own
+// known-answer tests over {A,B,D}, main.cpp:99-100).
+__device__ __forceinline__ uint32_t code_of(uint32_t c, const uint8_t* lut, int& bad) {
+  if (lut) {
+    const uint32_t v = lut[c];
+    bad |= v > 3;
+    return v & 3;
+  }
+  const uint32_t v = (c >> 1) & 3;
+  bad |= (c != ((0x47544341u >> (8 * v)) & 0xFFu));   // "ACTG"[v]
+  return v;
+}
+
+// Q side: one code byte per symbol (read once per band by the owning thread).
+__global__ void encode_q_kernel(const uint8_t* __restrict__ src, long long n, uint8_t* __restrict__ dst,
+                                const uint8_t* __restrict__ lut, int* status) {
+  int bad = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x * 16;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += stride) {
+    if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0)) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + i);        // coalesced 128-bit read
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o[k] |= code_of((w[k] >> (8 * b)) & 0xFF, lut, bad) << (8 * b);
+      }
+      *reinterpret_cast<uint4*>(dst + i) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (long long k = i; k < n && k < i + 16; ++k) dst[k] = (uint8_t)code_of(src[k], lut, bad);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status + 1, swb::STATUS_BAD_SYMBOL);
+}
+
+// T side: 32 symbols per 64-bit word, symbol p at bits 2*(p%32).
+__global__ void encode_t_kernel(const uint8_t* __restrict__ src, long long n, uint64_t* __restrict__ dst,
+                                const uint8_t* __restrict__ lut, int* status) {
+  int bad = 0;
+  const long long nwords = (n + 31) / 32;
+  for (long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x; wi < nwords;
+       wi += (long long)gridDim.x * blockDim.x) {
+    const long long base = wi * 32;
+    uint64_t out = 0;
+    if (base + 32 <= n && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0)) {
+      const uint4 a = *reinterpret_cast<const uint4*>(src + base);
+      const uint4 b = *reinterpret_cast<const uint4*>(src + base + 16);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          out |= (uint64_t)code_of((w[k] >> (8 * q)) & 0xFF, lut, bad) << (2 * (4 * k + q));
+    } else {
+      for (int k = 0; k < 32 && base + k < n; ++k) out |= (uint64_t)code_of(src[base + k], lut, bad) << (2 * k);
+    }
+    dst[wi] = out;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status + 1, swb::STATUS_BAD_SYMBOL);
+}
+
+// 256-bit presence map of the byte values in a buffer.
+__global__ void presence_kernel(const uint8_t* __restrict__ src, long long n, uint32_t* bitmap) {
+  __shared__ uint32_t local[8];
+  if (threadIdx.x < 8) local[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t c = src[i];
+    atomicOr(&local[c >> 5], 1u << (c & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && local[threadIdx.x]) atomicOr(&bitmap[threadIdx.x], local[threadIdx.x]);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+//  context
+// ---------------------------------------------------------------------------------------------
+struct swb200_ctx {
+  int device = 0;
+  int sms = 0;
+  std::mutex mu;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // grow-only device buffers
+  uint8_t* d_ascii = nullptr; size_t ascii_cap = 0;
+  uint8_t* d_q = nullptr; size_t q_cap = 0;
+  uint64_t* d_t = nullptr; size_t t_cap = 0;     // words
+  uint2* d_links = nullptr; size_t links_cap = 0;  // entries
+  uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
+  unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
+  int* d_result = nullptr;        // [0] score [1] status, [2..9] presence bitmap
+  uint8_t* d_lut = nullptr;       // 256 bytes
+  int* h_result = nullptr;        // pinned
+  unsigned epoch = 0;
+  swb200_run_info info{};
+};
+
+namespace {
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need, bool zero, cudaStream_t s) {
+  if (need <= cap) return SWB200_OK;
+  if (p) SWB_CUDA(cudaFree(p));
+  p = nullptr; cap = 0;
+  const size_t want = need + need / 4 + 1024;
+  cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+  if (e != cudaSuccess) return fail(SWB200_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  cap = want;
+  if (zero) SWB_CUDA(cudaMemsetAsync(p, 0, want * sizeof(T), s));
+  return SWB200_OK;
+}
+
+int check_params(const swb200_params& p) {
+  if (p.match < 0 || p.match > 100 || p.mismatch > 0 || p.mismatch < -100 || p.gap_init < 0 || p.gap_init > 100 ||
+      p.gap_ext < 0 || p.gap_ext > 100 || p.match + p.gap_init > 127)
+    return fail(SWB200_ERR_ARG, "scoring parameters outside the documented limits");
+  return SWB200_OK;
+}
+
+struct Plan {
+  int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine
+  int R, config, ctas;
+  bool swap;     // Q = seq2 instead of seq1
+};
+
+// Estimated cycles for one (R, config) choice: steps the slowest warp executes times cycles per step.
+// The constants come from bench/intpeak.cu and the first B200 sweeps (profiles/); they only steer the
+// choice, never the result.
+double estimate(long long LQ, long long LT, int mode, int R, int config, int sms) {
+  const int rpb = swb::rows_per_band(R, mode);
+  const long long NB = (LQ + rpb - 1) / rpb;
+  const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
+  const long long W = (long long)sms * wpc;
+  const long long rounds = (NB + W - 1) / W;
+  const long long active = std::min<long long>(NB, W);
+  const int skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const double per_row = mode == 1 ? 5.0 : 7.0;
+  const double instr = per_row * R + 12.0;                       // issue slots per step per warp
+  const double cyc_step = config == 1 ? std::max(instr * 1.25, 8.0 * R + 30.0)  // one warp per scheduler
+                                      : instr * 2.2;                             // two warps share a scheduler
+  const double steps = (double)rounds * (double)(LT + skew) + (double)active * (skew + 32 + 48);
+  return steps * cyc_step;
+}
+
+Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms) {
+  Plan pl{};
+  pl.swap = m > n;                         // stripe the longer sequence across lanes
+  const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
+  pl.mode = lanes == 32 ? 2 : ((p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0);
+  double best = 1e300;
+  for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
+    if (o.config && o.config != ci) continue;
+    for (int ri = 0; ri < swb::kNumRowChoices; ++ri) {
+      const int R = swb::kRowChoices[ri];
+      if (o.rows && o.rows != R) continue;
+      const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
+      if (e < best) { best = e; pl.R = R; pl.config = ci; }
+    }
+  }
+  if (best == 1e300) { pl.R = o.rows ? o.rows : 4; pl.config = o.config ? o.config : 1; }
+  pl.ctas = o.ctas;
+  return pl;
+}
+
+const void* kernel_for(const Plan& pl) {
+  switch (pl.mode) {
+    case 0: return swb::engine_kernel_mode0(pl.R, pl.config);
+    case 1: return swb::engine_kernel_mode1(pl.R, pl.config);
+    default: return swb::engine_kernel_mode2(pl.R, pl.config);
+  }
+}
+
+int log2_ceil(long long v) { int s = 0; while ((1LL << s) < v) ++s; return s; }
+
+// Encode + one engine run at a fixed lane width.  d_seq1/d_seq2 are device pointers.
+int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
+             const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
+             int* score, int* status) {
+  const Plan pl = make_plan(n, m, p, o, lanes, c->sms);
+  const void* kern = kernel_for(pl);
+  if (!kern) return fail(SWB200_ERR_ARG, "no kernel for rows=" + std::to_string(pl.R));
+  const uint8_t* dq = pl.swap ? d_seq2 : d_seq1;
+  const uint8_t* dt = pl.swap ? d_seq1 : d_seq2;
+  const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
+  const int wpc = swb::config_wpc(pl.config), slack = swb::config_slack(pl.config);
+  const int rpb = swb::rows_per_band(pl.R, pl.mode);
+  const long long NB = (LQ + rpb - 1) / rpb;
+  if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
+
+  int per_sm = 0;
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, 0));
+  if (per_sm < 1) return fail(SWB200_ERR_CUDA, "engine kernel does not fit on an SM");
+  long long ctas = std::min<long long>((NB + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
+  if (pl.ctas > 0) ctas = std::min<long long>(ctas, pl.ctas);
+  ctas = std::max<long long>(ctas, 1);
+  const int warps = (int)ctas * wpc;
+
+  const int skew = pl.mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const long long nsteps = ((LT + skew + swb::kChunk - 1) / swb::kChunk) * swb::kChunk;
+  const int ext_shift = log2_ceil(nsteps + swb::kChunk);
+  const long long ext_len = 1LL << ext_shift;
+  // inner rings: at most 256 laps (8-bit lap tag), at least 4096 entries
+  int link_shift = std::max(12, log2_ceil((nsteps + 255) / 256));
+  const long long link_len = 1LL << link_shift;
+
+  int rc;
+  if ((rc = grow(c->d_q, c->q_cap, (size_t)LQ + 64, false, s))) return rc;
+  if ((rc = grow(c->d_t, c->t_cap, (size_t)(LT / 32 + 8), false, s))) return rc;
+  const size_t links_need = (size_t)std::max(warps - 1, 1) * 2 * (size_t)link_len;
+  const size_t ext_need = 2 * (size_t)ext_len;
+  const bool links_fresh = links_need > c->links_cap, ext_fresh = ext_need > c->ext_cap;
+  if ((rc = grow(c->d_links, c->links_cap, links_need, true, s))) return rc;
+  if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
+  if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 2, false, s))) return rc;
+  (void)links_fresh; (void)ext_fresh;
+
+  // tags carry a 6-bit epoch; when it wraps, forget every old tag
+  c->epoch += 1;
+  if (c->epoch > 63) {
+    c->epoch = 1;
+    SWB_CUDA(cudaMemsetAsync(c->d_links, 0, c->links_cap * sizeof(uint2), s));
+    SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
+  }
+  SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 2) * sizeof(unsigned long long), s));
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 2 * sizeof(int), s));
+
+  const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
+  encode_q_kernel<<<eb, 256, 0, s>>>(dq, LQ, c->d_q, d_lut, c->d_result);
+  const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
+  encode_t_kernel<<<tb, 256, 0, s>>>(dt, LT, c->d_t, d_lut, c->d_result);
+  SWB_CUDA(cudaGetLastError());
+  c->info.aux_launches += 2;
+
+  swb::EngineParams P{};
+  P.q_codes = c->d_q; P.t_packed = c->d_t; P.LQ = LQ; P.LT = LT; P.NB = (int)NB;
+  P.ring_total = warps; P.ring_offset = 0; P.warps_local = warps;
+  P.links = c->d_links; P.link_mask = (unsigned)(link_len - 1); P.link_shift = link_shift;
+  P.progress = c->d_progress;
+  P.ext_in = c->d_ext; P.ext_out = c->d_ext; P.ext_mask = (unsigned)(ext_len - 1); P.ext_shift = ext_shift;
+  P.tag_base = c->epoch << 26; P.result = c->d_result;
+  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
+  P.spin_limit = 40LL * 1000 * 1000;
+  void* args[] = {&P};
+  SWB_CUDA(cudaEventRecord(c->ev0, s));
+  SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
+  SWB_CUDA(cudaEventRecord(c->ev1, s));
+  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  *score = c->h_result[0];
+  *status = c->h_result[1];
+  c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.linear = pl.mode == 1; c->info.rows = pl.R; c->info.config = pl.config;
+  c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
+  c->info.engine_ms = ms;
+  return SWB200_OK;
+}
+
+// Full policy for one pair whose bytes are in device memory.
+int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
+                        const swb200_params* pp, const swb200_options* oo, cudaStream_t s, int* score_out) {
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  const swb200_options o = oo ? *oo : swb200_options{};
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  if (n < 0 || m < 0 || !score_out) return fail(SWB200_ERR_ARG, "negative length or null output");
+  if (o.lanes != 0 && o.lanes != 16 && o.lanes != 32) return fail(SWB200_ERR_ARG, "lanes must be 0, 16 or 32");
+  c->info = swb200_run_info{};
+  c->info.cells = n * m;
+  if (n == 0 || m == 0) { *score_out = 0; return SWB200_OK; }   // both reference oracles return 0 here
+  SWB_CUDA(cudaSetDevice(c->device));
+
+  const uint8_t* lut = nullptr;
+  int lanes = o.lanes == 32 ? 32 : 16;
+  // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
+  // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
+  // leaving the range and we repeat in 32 bits (bit-exact either way).
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    int score = 0, status = 0;
+    if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status))) return rc;
+    if (status & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off timed out");
+    if (status & swb::STATUS_BAD_SYMBOL) {
+      if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
+      // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
+      SWB_CUDA(cudaMemsetAsync(c->d_result + 2, 0, 8 * sizeof(int), s));
+      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq1, n, reinterpret_cast<uint32_t*>(c->d_result + 2));
+      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq2, m, reinterpret_cast<uint32_t*>(c->d_result + 2));
+      c->info.aux_launches += 2;
+      SWB_CUDA(cudaMemcpyAsync(c->h_result + 2, c->d_result + 2, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      SWB_CUDA(cudaStreamSynchronize(s));
+      uint8_t table[256];
+      memset(table, 4, sizeof table);
+      int distinct = 0;
+      for (int v = 0; v < 256; ++v)
+        if ((reinterpret_cast<uint32_t*>(c->h_result + 2)[v >> 5] >> (v & 31)) & 1u) {
+          if (distinct < 4) table[v] = (uint8_t)distinct;
+          ++distinct;
+        }
+      if (distinct > 4)
+        return fail(SWB200_ERR_ALPHABET, "more than 4 distinct byte values (" + std::to_string(distinct) + ")");
+      SWB_CUDA(cudaMemcpyAsync(c->d_lut, table, 256, cudaMemcpyHostToDevice, s));
+      SWB_CUDA(cudaStreamSynchronize(s));
+      lut = c->d_lut;
+      continue;
+    }
+    if (status & swb::STATUS_S16_OVERFLOW) {
+      if (o.lanes == 16) return fail(SWB200_ERR_RANGE, "score leaves the 16-bit lane range");
+      lanes = 32;
+      continue;
+    }
+    *score_out = score;
+    return SWB200_OK;
+  }
+  return fail(SWB200_ERR_CUDA, "internal: retry budget exhausted");
+}
+
+std::mutex g_default_mu;
+swb200_ctx* g_default_ctx = nullptr;
+
+int default_ctx(swb200_ctx** out) {
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  if (!g_default_ctx) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int rc = swb200_ctx_create(dev, &g_default_ctx);
+    if (rc) return rc;
+  }
+  *out = g_default_ctx;
+  return SWB200_OK;
+}
+
+int legacy(const unsigned char* a, const unsigned char* b, int n, int m, const char* who) {
+  int score = 0;
+  const int rc = swb200_score(a, n, b, m, nullptr, &score);
+  if (rc != SWB200_OK) {
+    // The reference signature has no error channel: never return a made-up score.
+    fprintf(stderr, "libswb200: %s failed (%d): %s\n", who, rc, swb200_last_error());
+    abort();
+  }
+  return score;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+//  exported C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* swb200_last_error(void) { return g_err.c_str(); }
+
+int swb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
+  if (!ctx_out) return fail(SWB200_ERR_ARG, "null ctx_out");
+  *ctx_out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(SWB200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(SWB200_ERR_ARG, "device index out of range");
+  SWB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SWB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SWB200_ERR_CUDA, std::string("libswb200 is built for sm_100a (B200) only; found ") + prop.name);
+  int coop = 0;
+  SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(SWB200_ERR_CUDA, "device lacks cooperative launch");
+  swb200_ctx* c = new swb200_ctx();
+  c->device = device;
+  c->sms = prop.multiProcessorCount;
+  SWB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  SWB_CUDA(cudaEventCreate(&c->ev0));
+  SWB_CUDA(cudaEventCreate(&c->ev1));
+  SWB_CUDA(cudaMalloc(&c->d_result, 16 * sizeof(int)));
+  SWB_CUDA(cudaMalloc(&c->d_lut, 256));
+  SWB_CUDA(cudaMallocHost(&c->h_result, 16 * sizeof(int)));
+  *ctx_out = c;
+  return SWB200_OK;
+}
+
+void swb200_ctx_destroy(swb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_links); cudaFree(c->d_ext);
+  cudaFree(c->d_progress); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFreeHost(c->h_result);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int swb200_score_device(swb200_ctx* c, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2,
+                        long long m, const swb200_params* p, const swb200_options* opt, void* stream,
+                        int* score_out) {
+  if (!c) return fail(SWB200_ERR_ARG, "null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  return score_device_locked(c, d_seq1, n, d_seq2, m, p, opt, (cudaStream_t)stream, score_out);
+}
+
+int swb200_score_ex(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                    const swb200_params* p, const swb200_options* opt, int* score_out) {
+  if (n < 0 || m < 0 || !score_out || (n > 0 && !seq1) || (m > 0 && !seq2))
+    return fail(SWB200_ERR_ARG, "bad sequence arguments");
+  if (n == 0 || m == 0) {
+    if (p) { int rc = check_params(*p); if (rc) return rc; }
+    *score_out = 0;
+    return SWB200_OK;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->own_stream;
+  // both sequences into one staging buffer, 256-byte aligned so the encoders can use 128-bit reads
+  const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
+  if ((rc = grow(c->d_ascii, c->ascii_cap, off2 + (size_t)m + 256, false, s))) return rc;
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
+  return score_device_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, opt, s, score_out);
+}
+
+int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, int m, const swb200_params* p,
+                 int* score_out) {
+  return swb200_score_ex(seq1, n, seq2, m, p, nullptr, score_out);
+}
+
+int swb200_last_run(swb200_ctx* c, swb200_run_info* info) {
+  if (!info) return fail(SWB200_ERR_ARG, "null info");
+  if (!c) {
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  *info = c->info;
+  return SWB200_OK;
+}
+
+// ---- the reference's names (algoGPU.h:5-9, SmithDiagonalGPUrefactored.cu:174) ---------------------
+int SequentialSmithWatermanScoreGPU(unsigned char* seq1, unsigned char* seq2, int len1, int len2) {
+  return legacy(seq1, seq2, len1, len2, "SequentialSmithWatermanScoreGPU");
+}
+int SmithWatermanLazyGPU(const unsigned char* seq1, const unsigned char* seq2, int n, int m) {
+  return legacy(seq1, seq2, n, m, "SmithWatermanLazyGPU");
+}
+int SmithWatermanScoreCUDA(const unsigned char* seq1, const unsigned char* seq2, int n, int m) {
+  return legacy(seq1, seq2, n, m, "SmithWatermanScoreCUDA");
+}
+int SmithDiagonalGPU(unsigned char* seq1, unsigned char* seq2, int n, int m) {
+  return legacy(seq1, seq2, n, m, "SmithDiagonalGPU");
+}
+
+}  // extern "C"

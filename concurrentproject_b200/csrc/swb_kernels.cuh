@@ -1,0 +1,46 @@
+// swb_kernels.cuh -- __global__ wrappers of the wavefront engine and their lookup table.
+#pragma once
+#include "swb_engine.cuh"
+
+namespace swb {
+
+// config 1: 4 warps per CTA (one per SM scheduler), boundary value consumed one step late (SLACK 1)
+// config 2: 8 warps per CTA (two per scheduler), consumed in the same step (SLACK 0)
+constexpr int kNumConfigs = 2;
+SWB_HD int config_wpc(int config) { return config == 1 ? 4 : 8; }
+SWB_HD int config_slack(int config) { return config == 1 ? 1 : 0; }
+
+constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 12, 16};
+constexpr int kNumRowChoices = 8;
+
+// mode 0: s16x2 affine, 1: s16x2 linear (gap_init == gap_ext), 2: s32 affine
+const void* engine_kernel_mode0(int R, int config);
+const void* engine_kernel_mode1(int R, int config);
+const void* engine_kernel_mode2(int R, int config);
+
+#ifdef __CUDACC__
+template <int R, int MODE, int SLACK, int WPC>
+__global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineParams P) {
+  __shared__ WarpSmem sm[WPC];
+  WarpCtx w{(int)(threadIdx.x & 31)};
+  const int wi = (int)(threadIdx.x >> 5);
+  const int lw = (int)blockIdx.x * WPC + wi;
+  if constexpr (MODE == 2) engine_warp_s32<R, SLACK>(P, w, lw, &sm[wi]);
+  else engine_warp_s16<R, MODE, SLACK>(P, w, lw, &sm[wi]);
+}
+
+template <int MODE>
+static const void* engine_kernel_lookup(int R, int config) {
+#define SWB_CASE(RR)                                                             \
+  case RR:                                                                       \
+    return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
+                       : (const void*)sw_engine_kernel<RR, MODE, 0, 8>;
+  switch (R) {
+    SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16)
+    default: return nullptr;
+  }
+#undef SWB_CASE
+}
+#endif
+
+}  // namespace swb

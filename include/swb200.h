@@ -1,0 +1,98 @@
+/*
+ * swb200.h -- C ABI of libswb200.so: B200-native score-only Smith-Waterman/Gotoh.
+ *
+ * The drop-in boundary is the reference's own GPU header, algoGPU.h:5-9 (three extern "C"
+ * functions: two host byte sequences in, one int local-alignment score out) plus the fourth symbol
+ * of SmithDiagonalGPUrefactored.cu:174.  Those four names are declared in include/algoGPU.h and
+ * exported by the library with the reference's exact signatures; TestFileWithGPU.cpp:82,87,92
+ * links against them unchanged.  Everything below is additive: runtime scoring
+ * parameters (the reference hard-codes them per file, main.cpp:20-23), error codes (the reference
+ * has no error channel), device-resident inputs, batches, banded alignment, multi-GPU stripes.
+ *
+ * Plain C, plain pointers and sizes; no C++ or torch types cross this boundary.
+ */
+#ifndef SWB200_H
+#define SWB200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SWB200_API __attribute__((visibility("default")))
+#else
+#define SWB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* MATCH / MISMATCH / G_INIT / G_EXT of main.cpp:20-23, as data.  A gap of length k costs
+ * gap_init + (k-1)*gap_ext (main.cpp:57-58).  Limits: |match|,|mismatch| <= 100,
+ * 0 <= gap_ext, gap_init <= 100, match + gap_init <= 127, mismatch <= 0 <= match. */
+typedef struct {
+  int match;
+  int mismatch;
+  int gap_init;
+  int gap_ext;
+} swb200_params;
+
+/* Kernel selection; all zero = automatic.  Exposed for benchmarking and tests. */
+typedef struct {
+  int lanes;       /* 0 auto (packed 16-bit, 32-bit re-run if the score leaves the s16 range), 16, 32 */
+  int rows;        /* R: DP rows per sub-lane, one of 1,2,3,4,6,8,12,16; 0 auto */
+  int config;      /* 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA) */
+  int ctas;        /* thread blocks (<= co-resident limit); 0 auto */
+  int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
+  int reserved[3];
+} swb200_options;
+
+/* Return codes (legacy names have no error channel: they print and abort instead). */
+#define SWB200_OK 0
+#define SWB200_ERR_CUDA (-1)      /* a CUDA call failed; see swb200_last_error() */
+#define SWB200_ERR_ARG (-2)       /* bad argument or parameter outside the documented limits */
+#define SWB200_ERR_ALPHABET (-3)  /* more than 4 distinct byte values in the two sequences */
+#define SWB200_ERR_TIMEOUT (-4)   /* a boundary hand-off never arrived (peer GPU gone) */
+#define SWB200_ERR_NOMEM (-5)
+#define SWB200_ERR_RANGE (-6)     /* score does not fit the requested lane width */
+
+SWB200_API const char* swb200_last_error(void);
+SWB200_API int swb200_device_count(void);
+
+/* ---- one pair, HOST buffers: the call behind the four legacy names ------------------------------
+ * seq1/seq2: raw bytes, not NUL-terminated, caller-owned, never modified (algoGPU.h:5-9).
+ * n = len(seq1), m = len(seq2); n == 0 or m == 0 scores 0.  p == NULL means 1/-1/1/1. */
+SWB200_API int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, int m,
+                 const swb200_params* p, int* score_out);
+SWB200_API int swb200_score_ex(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                    const swb200_params* p, const swb200_options* opt, int* score_out);
+
+/* ---- handle API: sequences already resident in HBM ------------------------------------------------ */
+typedef struct swb200_ctx swb200_ctx;
+SWB200_API int swb200_ctx_create(int device, swb200_ctx** ctx_out);
+SWB200_API void swb200_ctx_destroy(swb200_ctx* ctx);
+
+/* d_seq1/d_seq2: DEVICE pointers to raw bytes.  stream: a cudaStream_t (NULL = default stream).
+ * All kernels are enqueued on `stream`; the call returns after the 16-byte result came back. */
+SWB200_API int swb200_score_device(swb200_ctx* ctx, const unsigned char* d_seq1, long long n,
+                        const unsigned char* d_seq2, long long m, const swb200_params* p,
+                        const swb200_options* opt, void* stream, int* score_out);
+
+/* What the last swb200_score*_ call on this context actually ran. */
+typedef struct {
+  int lanes;            /* 16 or 32 */
+  int linear;           /* 1 if the gap_init == gap_ext kernel was used */
+  int rows;             /* R */
+  int config;
+  int ctas, warps;      /* launch shape */
+  int bands;            /* DP bands of the pair */
+  int engine_launches;  /* wavefront kernels launched (2 when an s16 run was repeated in s32) */
+  int aux_launches;     /* encode / presence kernels launched */
+  long long cells;      /* n*m */
+  float engine_ms;      /* device time of the last wavefront kernel (CUDA events on its stream) */
+} swb200_run_info;
+SWB200_API int swb200_last_run(swb200_ctx* ctx, swb200_run_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

@@ -1,0 +1,90 @@
+"""Runs the product's wavefront engine body on CPU threads (tests/emu/engine_emu.cu) and compares
+with the oracle.  This is how the hand-off protocol (tags, ring laps, back-pressure, ring
+wrap-around over several rounds, multi-GPU ring) is covered without a GPU; the same source is what
+the sm_100a kernels compile.  Needs nvcc (host compile only)."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from concurrentproject_b200 import rng
+
+EMU_DIR = Path(__file__).resolve().parent / "emu"
+EMU = EMU_DIR / "engine_emu"
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = EMU_DIR / "engine_emu.cu"
+    hdrs = list((EMU_DIR.parent.parent / "concurrentproject_b200" / "csrc").glob("swb_*.cuh"))
+    if not EMU.exists() or EMU.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
+        subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(EMU),
+                        str(src), "-lpthread"], check=True, cwd=EMU_DIR)
+
+    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp")):
+        qf, tf = tmp / "swb_emu_q.bin", tmp / "swb_emu_t.bin"
+        qf.write_bytes(bytes(q)); tf.write_bytes(bytes(t))
+        ma, mi, gi, ge = p
+        out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],
+                             capture_output=True, text=True, timeout=900, check=True).stdout
+        d = dict(kv.split("=") for kv in out.split())
+        return int(d["score"]), int(d["status"])
+    return run
+
+
+def planted(seed, n, sub=0.06, indel=0.03):
+    a = rng.random_acgt(seed, 0, n)
+    return a, rng.mutate(a, seed, 1, sub, indel)
+
+
+@pytest.mark.parametrize("mode,slack", [(0, 1), (0, 0), (2, 1), (2, 0)])
+def test_affine_engine_small(emu, mode, slack):
+    for k, (n, R, W, G, p) in enumerate([(300, 1, 2, 1, O.DEFAULT), (700, 2, 3, 1, (2, -3, 5, 1)), (900, 3, 2, 2, (5, -4, 11, 1)),
+                                         (450, 1, 1, 1, (2, -1, 3, 1)), (1200, 4, 2, 1, (1, -1, 4, 2))]):
+        a, b = planted(100 + k, n)
+        assert emu(a, b, R, mode, slack, W, G, p) == (O.gotoh_rolling(a, b, p), 0), (n, R, W, G, p)
+        assert emu(b, a, R, mode, slack, W, G, p) == (O.gotoh_rolling(a, b, p), 0)
+
+
+@pytest.mark.parametrize("slack", [0, 1])
+def test_linear_engine_small(emu, slack):
+    for k, (n, R, W, G, p) in enumerate([(300, 1, 2, 1, O.DEFAULT), (800, 2, 3, 2, (3, -2, 2, 2)), (1000, 8, 1, 1, (1, -3, 1, 1))]):
+        a, b = planted(200 + k, n)
+        assert emu(a, b, R, 1, slack, W, G, p) == (O.gotoh_rolling(a, b, p), 0)
+
+
+def test_edge_shapes(emu):
+    for q, t in [(b"A", b"A"), (b"A", b"G"), (b"ACGT" * 16, b"A"), (b"A", b"ACGT" * 16), (b"A" * 129, b"A" * 129),
+                 (b"A" * 200, b"T" * 200), (b"ACGT" * 50, b"GCTA" * 50 + b"G")]:
+        for mode in (0, 1, 2):
+            assert emu(q, t, 1, mode, 1, 2, 1) == (O.gotoh_rolling(q, t), 0), (q[:8], t[:8], mode)
+
+
+def test_many_rounds_ring_wraparound(emu):
+    # 14 bands on a ring of 3 warps: each warp runs several bands, the last warp feeds the first
+    a, b = planted(300, 64 * 14 - 5)
+    assert emu(a, b, 1, 0, 1, 3, 1) == (O.gotoh_rolling(a, b), 0)
+    assert emu(a, b, 1, 2, 0, 3, 2) == (O.gotoh_rolling(a, b), 0)
+
+
+@pytest.mark.slow
+def test_ring_laps_and_backpressure(emu):
+    # T longer than the link ring: entries are overwritten lap after lap, producer must respect progress
+    a = rng.random_acgt(400, 0, 150)
+    t = rng.random_acgt(400, 1, 9000)
+    t[3000:3140] = a[:140]
+    assert emu(a, t, 1, 0, 1, 3, 1, link_len=2048) == (O.gotoh_rolling(a, t), 0)
+
+
+def test_s16_overflow_is_flagged(emu):
+    # identical sequences longer than the s16 range cannot be scored in packed 16-bit lanes: the
+    # engine must say so (status bit 1) instead of returning a wrapped score
+    a = np.frombuffer(b"ACGT" * 82, dtype=np.uint8)
+    score, status = emu(a, a, 1, 0, 1, 1, 1, p=(100, -1, 1, 1))
+    assert status & 1
+    assert emu(a, a, 1, 2, 1, 1, 1, p=(100, -1, 1, 1)) == (100 * 328, 0)

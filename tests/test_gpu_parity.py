@@ -1,0 +1,152 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/swb200.h, include/algoGPU.h),
+against the reference's golden vectors and against the CPU oracle on the same seeded inputs.
+Bit-exact: every comparison is integer equality."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import fixture_pair, load_json, mt_pairs
+from concurrentproject_b200 import rng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from concurrentproject_b200 import api as _api
+    return _api
+
+
+LEGACY = ("SequentialSmithWatermanScoreGPU", "SmithWatermanLazyGPU", "SmithWatermanScoreCUDA", "SmithDiagonalGPU")
+
+
+def planted(seed, n, sub=0.06, indel=0.03):
+    a = rng.random_acgt(seed, 0, n)
+    return a, rng.mutate(a, seed, 1, sub, indel)
+
+
+def test_known_answer_tables_through_legacy_names(api):
+    for c in load_json("kat.json"):
+        distinct = len(set(c["seq1"]) | set(c["seq2"]))
+        for name in LEGACY:
+            if distinct > 4:
+                continue
+            assert getattr(api, name)(c["seq1"], c["seq2"]) == c["score"], (name, c["source"])
+
+
+def test_more_than_four_symbols_is_an_error_not_a_wrong_score(api):
+    with pytest.raises(api.SwbError) as e:
+        api.score("GATTACA", "GCATGCU")
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("L", [32, 516, 4096])
+def test_reference_recorded_seeded_scores(api, L):
+    # cudaSmithM.cu:285-294 / 314-323 / 342-351: the numbers the reference's own GPU run printed
+    for a, b, want in mt_pairs(L):
+        for name in LEGACY:
+            assert getattr(api, name)(a, b, len(a), len(b)) == want
+
+
+def test_reference_fixture_scores_default_params(api):
+    for c in load_json("ref_scores_default.json"):
+        a, b = fixture_pair(c)
+        assert api.score(a, b) == c["score"], c
+        if c["n"] <= 4100:
+            assert api.score(a, b, no_linear=True) == c["score"], c
+            assert api.score(a, b, lanes=32) == c["score"], c
+
+
+def test_reference_fixture_scores_other_params(api):
+    for c in load_json("ref_scores_params.json"):
+        a, b = fixture_pair(c)
+        p = tuple(c["params"])
+        assert api.score(a, b, p) == c["score_main"], c            # contract: main.cpp, not lazySmith.cpp
+        assert api.score(a, b, p, lanes=32) == c["score_main"], c
+
+
+@pytest.mark.parametrize("config", [1, 2])
+@pytest.mark.parametrize("lanes,no_linear", [(16, False), (16, True), (32, True)])
+def test_every_kernel_variant_against_oracle(api, config, lanes, no_linear):
+    a, b = planted(500, 3000)
+    c, d = rng.random_acgt(501, 0, 2100), rng.random_acgt(501, 1, 5000)
+    for p in (O.DEFAULT, (2, -3, 5, 1)):
+        if p[2] != p[3] and not no_linear:
+            continue
+        w1, w2 = O.gotoh_rolling(a, b, p), O.gotoh_rolling(c, d, p)
+        for rows in (1, 2, 3, 4, 6, 8, 12, 16):
+            assert api.score(a, b, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w1, (rows, p)
+            assert api.score(c, d, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w2, (rows, p)
+            assert api.score(d, c, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w2, (rows, p)
+
+
+def test_many_rounds_on_few_ctas(api):
+    # force the ring to wrap: 3 CTAs, many bands
+    a, b = planted(510, 20000, 0.1, 0.04)
+    want = O.gotoh_mt(a, b)
+    for lanes in (16, 32):
+        assert api.score(a, b, lanes=lanes, rows=2, config=1, ctas=3, no_linear=True) == want
+        assert api.score(a, b, lanes=lanes, rows=1, config=2, ctas=2, no_linear=True) == want
+
+
+def test_edge_shapes(api):
+    for q, t in [(b"", b""), (b"", b"ACGT"), (b"ACGT", b""), (b"A", b"A"), (b"A", b"G"), (b"ACGT" * 16, b"A"),
+                 (b"A", b"ACGT" * 16), (b"A" * 5000, b"A" * 5000), (b"A" * 2000, b"T" * 2000),
+                 (b"ACGT" * 100, b"GCTA" * 100 + b"G"), (b"C" * 70000, b"C" * 3)]:
+        assert api.score(q, t) == O.gotoh_rolling(q, t), (q[:8], len(q), len(t))
+
+
+def test_other_alphabets_are_remapped(api):
+    # the reference compares raw bytes; its own tests use {A,B,D} (main.cpp:99-100)
+    assert api.score("ABDAAADB", "ADDBAABB") == 2
+    assert api.score("acgtacgtacgt", "acgtacgtacgt") == 12
+    a = np.frombuffer(bytes([0, 255, 7, 0, 0, 255, 7, 7, 255] * 30), dtype=np.uint8)
+    b = np.frombuffer(bytes([255, 7, 0, 0, 255, 255, 7] * 41), dtype=np.uint8)
+    assert api.score(a, b) == O.gotoh_rolling(a, b)
+    assert api.score("AAAA", "aaaa") == 0   # case matters, as in the reference's byte compare
+
+
+def test_scores_beyond_the_s16_range_rerun_in_32_bit(api):
+    a = rng.random_acgt(520, 0, 40000)
+    assert api.score(a, a) == 40000                      # analytic: identical sequences score MATCH*N
+    assert api.last_run()["lanes"] == 32 and api.last_run()["engine_launches"] == 2
+    b = a.copy(); b[20000:20010] = (b[20000:20010] ^ 6)   # a 10-base substitution block in the middle
+    assert api.score(a, b) == O.gotoh_mt(a, b)
+    with pytest.raises(api.SwbError) as e:
+        api.score(a, a, lanes=16)
+    assert e.value.code == -6
+
+
+def test_device_resident_inputs(api):
+    import torch
+    a, b = planted(530, 30000, 0.08, 0.03)
+    ta = torch.from_numpy(a.copy()).cuda(); tb = torch.from_numpy(b.copy()).cuda()
+    ctx = api.Context(0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = ctx.score_device(ta.data_ptr(), ta.numel(), tb.data_ptr(), tb.numel(), stream=s.cuda_stream)
+    assert got == O.gotoh_mt(a, b)
+    info = ctx.last_run()
+    assert info["engine_launches"] == 1 and info["cells"] == len(a) * len(b)
+    ctx.close()
+
+
+def test_cfg2_full_size_pair(api):
+    """BASELINE config 2: one 100 000 x 100 000 pair; expectation = the unmodified reference's LazySmith
+    (tests/golden/ref_scores_default.json, generated by make_golden.py --big)."""
+    case = [c for c in load_json("ref_scores_default.json") if c.get("config") == "cfg2"]
+    assert case, "cfg2 fixture missing"
+    a, b = fixture_pair(case[0])
+    assert api.score(a, b) == case[0]["score"]
+    assert api.score(a, b, no_linear=True) == case[0]["score"]
+    assert api.score(a, b, lanes=32) == case[0]["score"]
+    assert api.score(b, a) == case[0]["score"]           # argument-swap symmetry at full size
+
+
+def test_size_independent_properties_at_scale(api):
+    n = 300000
+    a = rng.random_acgt(540, 0, n)
+    assert api.score(a, a) == n                                            # identical -> MATCH*N
+    assert api.score(b"A" * n, b"C" * n) == 0                               # disjoint alphabets -> 0
+    b = np.concatenate([a[:150000], a[150007:]])                            # 7 deleted bases: one gap of 7
+    assert api.score(a, b) == max(150000, (n - 7) - (1 + 6 * 1))
