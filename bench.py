@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the score-only Smith-Waterman/Gotoh hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|...]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload is
+BASELINE config 2: one 100 000 x 100 000 pair of seeded random ACGT (seed 2), parameters 1/-1/1/1;
+its score is checked against the committed golden value (the unmodified reference's LazySmith) on
+every step.  One JSON line goes to stdout (rank 0):
+  value      device-resident GCUPS: inputs already in HBM, CUDA events around each step
+             (encode kernels + wavefront kernel + 40-byte result copy), L2 flushed between steps
+  e2e        the same metric through the host-buffer C ABI call the reference harness makes
+             (algoGPU.h SmithWatermanScoreCUDA): H2D + encode + kernel + D2H, wall clock
+  roofline   the wavefront kernel alone against the integer-ALU (DPX) issue-rate roofline of
+             SURVEY.md 8d: 148 SMs x f_clk x L x V / 7, L measured by bench/intpeak.cu
+  cpu_baseline  the reference's own CPU path (oracle/_ref/libref.so = unmodified
+             lazySmith_parallel_threads.cpp) timed on this box's host cores, bounded sample
+--impl reference runs only that CPU path, as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from concurrentproject_b200 import rng  # noqa: E402
+
+METRIC = "GCUPS (affine Smith-Waterman score, cells/s/1e9)"
+DPX_LANE_INSTR_PER_CLK_PER_SM = 64.0   # L: profiles/r01_intpeak.jsonl (VIMNMX3/VIADDMNMX.S16x2 streams, B200)
+INSTR_PER_CELL_VECTOR = 7.0            # SURVEY.md 8d contract figure
+N_SM = 148
+
+WORKLOADS = {
+    # name: (n, m, seed, description)
+    "cfg1": (1000, 1000, 1, "10 pairs 1000x1000 (TestFile.cpp default)"),
+    "cfg2": (100000, 100000, 2, "single pair 100000x100000, seed 2, MATCH=1 MISMATCH=-1 GAP_INIT=1 GAP_EXT=1"),
+    "n1m": (1000000, 1000000, 6, "single pair 1000000x1000000, seed 6"),
+}
+
+
+def golden_score(name):
+    if name != "cfg2":
+        return None
+    cases = json.loads((ROOT / "tests" / "golden" / "ref_scores_default.json").read_text())
+    for c in cases:
+        if c.get("config") == "cfg2":
+            return c["score"]
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_gcups(n_sample, seed, repeats=1):
+    """Times the reference's own CPU path on a bounded sample of the workload; returns (gcups, kind, cores, text)."""
+    import oracle_lib as O
+    a = rng.random_acgt(seed, 0, n_sample)
+    b = rng.random_acgt(seed, 1, n_sample)
+    if O.ref_available():
+        kind, fn = "reference", lambda: O.ref_call("ref_ParallelLazySmith_threads", a, b)
+        what = "unmodified lazySmith_parallel_threads.cpp (ParallelLazySmith_threads, default args: sequential, lazySmith_parallel_threads.cpp:78-81)"
+    else:
+        kind, fn = "port", lambda: O.lazy_smith(a, b)
+        what = "oracle port of LazySmith (oracle/_ref not present)"
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        s = fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_sample * n_sample / best / 1e9, kind, 1, f"{n_sample}x{n_sample} prefix of the workload pair, {what}; score {s}; host has {os.cpu_count()} cores"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, m, seed, desc = WORKLOADS[args.workload]
+    n_s = min(n, 8000)
+    for _ in range(args.warmup):
+        cpu_reference_gcups(2000, seed)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        g, kind, cores, text = cpu_reference_gcups(n_s, seed)
+        vals.append(g)
+    dt = time.perf_counter() - t0
+    value = n_s * n_s * args.steps / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": round(value, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
+            "e2e": {"value": round(value, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from concurrentproject_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m, seed, desc = WORKLOADS[args.workload]
+    # weak scaling over pairs: rank r scores its own pair (streams 2r, 2r+1); no data-path collective
+    a_h = rng.random_acgt(seed, 2 * rank, n)
+    b_h = rng.random_acgt(seed, 2 * rank + 1, m)
+    a_d = torch.from_numpy(a_h.copy()).cuda()
+    b_d = torch.from_numpy(b_h.copy()).cuda()
+    want = golden_score(args.workload) if rank == 0 else None
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step_device():
+        return ctx.score_device(a_d.data_ptr(), n, b_d.data_ptr(), m, stream=stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        s = step_device()
+    if want is not None and s != want:
+        raise SystemExit(f"bench.py: score {s} != golden {want}")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    engine_ms, launches = [], 0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # L2 flush between timed steps (outside the event pair)
+        ev[k][0].record(stream)
+        s = step_device()
+        ev[k][1].record(stream)
+        info = ctx.last_run()
+        engine_ms.append(info["engine_ms"])
+        launches += info["engine_launches"] + info["aux_launches"]
+        if want is not None and s != want:
+            raise SystemExit(f"bench.py: score {s} != golden {want}")
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # end to end through the host-buffer call of the reference harness (TestFileWithGPU.cpp:92):
+    # H2D of both sequences + encode + wavefront kernel + D2H of the result, wall clock per call
+    for _ in range(2):
+        api.SmithWatermanScoreCUDA(a_h, b_h)
+    e2e_total = 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        s2 = api.SmithWatermanScoreCUDA(a_h, b_h)
+        e2e_total += time.perf_counter() - t1
+        if want is not None and s2 != want:
+            raise SystemExit(f"bench.py: e2e score {s2} != golden {want}")
+
+    t = torch.tensor([dev_ms, e2e_total * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    cells = float(n) * float(m)
+    value = cells * world * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_val = cells * world * args.steps / (e2e_ms * 1e-3) / 1e9
+    if rank == 0:
+        k_ms = float(np.mean(engine_ms))
+        f_mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965
+        vwidth = 2 if info["lanes"] == 16 else 1
+        peak = N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
+        achieved = cells / (k_ms * 1e-3) / 1e9
+        cpu_g, kind, cores, text = cpu_reference_gcups(min(n, 12000), seed)
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "s16x2" if info["lanes"] == 16 else "s32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "pairs_per_gpu": 1,
+                       "l2": "flushed between timed steps (256 MiB write)", "kernel": info,
+                       "score_checked_against_golden": want is not None},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(n + m), "d2h_bytes_per_step": 40,
+                    "call": "SmithWatermanScoreCUDA(host bytes) via libswb200.so C ABI, wall clock"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); peak = 148 SM x {f_mhz} MHz x "
+                                 f"L={DPX_LANE_INSTR_PER_CLK_PER_SM:.0f} DPX lane-instr/clk/SM (measured, bench/intpeak.cu) x V={vwidth} / 7 "
+                                 "instr per cell vector (SURVEY.md 8d); not an HBM- or tensor-bound kernel"},
+            "cpu_baseline": {"value": round(cpu_g, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

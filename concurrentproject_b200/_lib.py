@@ -19,7 +19,7 @@ class Params(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("lanes", C.c_int), ("rows", C.c_int), ("config", C.c_int), ("ctas", C.c_int),
-                ("no_linear", C.c_int), ("reserved", C.c_int * 3)]
+                ("no_linear", C.c_int), ("orient", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class RunInfo(C.Structure):

@@ -185,7 +185,7 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
 
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms) {
   Plan pl{};
-  pl.swap = m > n;                         // stripe the longer sequence across lanes
+  pl.swap = o.orient ? o.orient == 2 : m > n;   // default: stripe the longer sequence across lanes
   const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
   pl.mode = lanes == 32 ? 2 : ((p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0);
   double best = 1e300;
@@ -263,7 +263,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
   }
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 2) * sizeof(unsigned long long), s));
-  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 2 * sizeof(int), s));
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
   encode_q_kernel<<<eb, 256, 0, s>>>(dq, LQ, c->d_q, d_lut, c->d_result);
@@ -280,17 +280,37 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   P.ext_in = c->d_ext; P.ext_out = c->d_ext; P.ext_mask = (unsigned)(ext_len - 1); P.ext_shift = ext_shift;
   P.tag_base = c->epoch << 26; P.result = c->d_result;
   P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
-  P.spin_limit = 40LL * 1000 * 1000;
+  P.spin_limit = getenv("SWB200_SPIN_LIMIT") ? atoll(getenv("SWB200_SPIN_LIMIT")) : 40LL * 1000 * 1000;
+  P.dbg = getenv("SWB200_DBG") ? atoi(getenv("SWB200_DBG")) : 0;
+  long long* d_prof = nullptr;
+  if (getenv("SWB200_PROF")) {
+    SWB_CUDA(cudaMalloc(&d_prof, (size_t)warps * 4 * sizeof(long long)));
+    SWB_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)warps * 4 * sizeof(long long), s));
+  }
+  P.prof = d_prof;
   void* args[] = {&P};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
   SWB_CUDA(cudaEventRecord(c->ev1, s));
-  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 10 * sizeof(int), cudaMemcpyDeviceToHost, s));
   SWB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   *score = c->h_result[0];
   *status = c->h_result[1];
+  if (d_prof) {
+    std::vector<long long> hp((size_t)warps * 4);
+    cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    for (int wv = 0; wv < warps && wv < 12; ++wv)
+      fprintf(stderr, "prof warp %d: prologue %.0f cyc/chunk, steps %.0f cyc/chunk, failed polls %.2f/chunk, chunks %lld\n", wv,
+              hp[4 * wv + 3] ? (double)hp[4 * wv] / hp[4 * wv + 3] : 0.0, hp[4 * wv + 3] ? (double)hp[4 * wv + 1] / hp[4 * wv + 3] : 0.0,
+              hp[4 * wv + 3] ? (double)hp[4 * wv + 2] / hp[4 * wv + 3] : 0.0, hp[4 * wv + 3]);
+  }
+  if ((*status & swb::STATUS_SPIN_TIMEOUT) && getenv("SWB200_DEBUG"))
+    fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u]\n",
+            c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
+            c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch);
   c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.linear = pl.mode == 1; c->info.rows = pl.R; c->info.config = pl.config;
   c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
   c->info.engine_ms = ms;
@@ -323,17 +343,17 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
     if (status & swb::STATUS_BAD_SYMBOL) {
       if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
       // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
-      SWB_CUDA(cudaMemsetAsync(c->d_result + 2, 0, 8 * sizeof(int), s));
-      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq1, n, reinterpret_cast<uint32_t*>(c->d_result + 2));
-      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq2, m, reinterpret_cast<uint32_t*>(c->d_result + 2));
+      SWB_CUDA(cudaMemsetAsync(c->d_result + 16, 0, 8 * sizeof(int), s));
+      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq1, n, reinterpret_cast<uint32_t*>(c->d_result + 16));
+      presence_kernel<<<2 * c->sms, 256, 0, s>>>(d_seq2, m, reinterpret_cast<uint32_t*>(c->d_result + 16));
       c->info.aux_launches += 2;
-      SWB_CUDA(cudaMemcpyAsync(c->h_result + 2, c->d_result + 2, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      SWB_CUDA(cudaMemcpyAsync(c->h_result + 16, c->d_result + 16, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
       SWB_CUDA(cudaStreamSynchronize(s));
       uint8_t table[256];
       memset(table, 4, sizeof table);
       int distinct = 0;
       for (int v = 0; v < 256; ++v)
-        if ((reinterpret_cast<uint32_t*>(c->h_result + 2)[v >> 5] >> (v & 31)) & 1u) {
+        if ((reinterpret_cast<uint32_t*>(c->h_result + 16)[v >> 5] >> (v & 31)) & 1u) {
           if (distinct < 4) table[v] = (uint8_t)distinct;
           ++distinct;
         }
@@ -418,9 +438,9 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
   SWB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   SWB_CUDA(cudaEventCreate(&c->ev0));
   SWB_CUDA(cudaEventCreate(&c->ev1));
-  SWB_CUDA(cudaMalloc(&c->d_result, 16 * sizeof(int)));
+  SWB_CUDA(cudaMalloc(&c->d_result, 32 * sizeof(int)));
   SWB_CUDA(cudaMalloc(&c->d_lut, 256));
-  SWB_CUDA(cudaMallocHost(&c->h_result, 16 * sizeof(int)));
+  SWB_CUDA(cudaMallocHost(&c->h_result, 32 * sizeof(int)));
   *ctx_out = c;
   return SWB200_OK;
 }

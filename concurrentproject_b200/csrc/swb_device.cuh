@@ -49,7 +49,10 @@ SWB_HD int max3relu32(int a, int b, int c) { return __vimax3_s32_relu(a, b, c); 
 
 SWB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #if SWB_DEVICE_CODE
-  return __byte_perm(a, b, sel);
+  // not __byte_perm(): that intrinsic masks the selector with 0x7777 and loses the sign-replicate bit
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 #else
   // PTX prmt.b32 default mode: nibble k of sel picks byte (n&7) of {b,a}; bit 3 replicates its sign.
   uint64_t pool = ((uint64_t)b << 32) | a;
@@ -69,7 +72,7 @@ SWB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // a single aligned 8-byte access is indivisible, so no fence is needed between value and tag.
 SWB_HD void st_entry(uint2* p, uint32_t value, uint32_t tag) {
 #if SWB_DEVICE_CODE
-  asm volatile("st.global.relaxed.sys.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(value), "r"(tag) : "memory");
+  asm volatile("st.global.relaxed.sys.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(value), "r"(tag));
 #else
   uint64_t v = ((uint64_t)tag << 32) | value;
   reinterpret_cast<std::atomic<uint64_t>*>(p)->store(v, std::memory_order_release);
@@ -79,12 +82,23 @@ SWB_HD void st_entry(uint2* p, uint32_t value, uint32_t tag) {
 SWB_HD uint2 ld_entry(const uint2* p) {
 #if SWB_DEVICE_CODE
   uint2 r;
-  asm volatile("ld.global.relaxed.sys.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  asm volatile("ld.global.relaxed.sys.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 #else
   uint64_t v = reinterpret_cast<const std::atomic<uint64_t>*>(p)->load(std::memory_order_acquire);
   uint2 r; r.x = (uint32_t)v; r.y = (uint32_t)(v >> 32);
   return r;
+#endif
+}
+
+// Read-only data fetched well before use: volatile so the compiler keeps the load where it is issued.
+SWB_HD uint64_t ld_early_u64(const uint64_t* p) {
+#if SWB_DEVICE_CODE
+  uint64_t v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+#else
+  return *p;
 #endif
 }
 
@@ -150,6 +164,7 @@ struct WarpCtx {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int reduce_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
   __device__ __forceinline__ int any(int pred) const { return __any_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ int all(int pred) const { return __all_sync(0xffffffffu, pred); }
 };
 #else
 // Host emulation: 32 threads per warp, a pthread barrier at every warp-synchronous point.
@@ -176,6 +191,7 @@ struct WarpCtx {
     pthread_barrier_wait(&ws->bar);
     return r;
   }
+  int all(int pred) const { return !any(!pred); }
   int any(int pred) const {
     ws->slot[lane] = (uint32_t)(pred != 0);
     pthread_barrier_wait(&ws->bar);

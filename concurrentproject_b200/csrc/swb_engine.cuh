@@ -52,6 +52,8 @@ struct EngineParams {
   int* result;                  // [0] best score (atomicMax), [1] status bits (atomicOr)
   int match, mismatch, gap_init, gap_ext;
   long long spin_limit;         // polls before a waiting warp gives up (sets STATUS_SPIN_TIMEOUT)
+  int dbg;                      // timing experiments only: 1 = no boundary stores, 2 = no boundary polls
+  long long* prof;              // optional [warps_local][4]: cycles in prologue, cycles in steps, failed polls, chunks
 };
 
 struct WarpSmem {
@@ -80,19 +82,59 @@ struct Waiter {
   bool aborted;
 };
 
+// First lane that gives up leaves a post-mortem in result[3..]: who waited for what.
+SWB_HD void record_timeout(const EngineParams& P, int kind, long long a, long long b, long long c, long long d) {
+#if SWB_DEVICE_CODE
+  if (atomicCAS(P.result + 3, 0, kind) == 0) {
+    P.result[4] = (int)a; P.result[5] = (int)b; P.result[6] = (int)c; P.result[7] = (int)d;
+    P.result[8] = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  }
+#else
+  (void)P; (void)kind; (void)a; (void)b; (void)c; (void)d;
+#endif
+}
+
 // Wait until the entry for producer step j of band `tagband` is present; returns its value.
-SWB_HD uint32_t wait_entry(const EngineParams& P, const uint2* slot, uint32_t want_tag, Waiter& wt) {
-  uint2 e = ld_entry(slot);
-  while (e.y != want_tag && !wt.aborted) {
-    if (--wt.budget < 0 || (((wt.budget & 1023) == 0) && (ld_flag(P.result + 1) & STATUS_SPIN_TIMEOUT))) {
+// Warp-uniform wait: every lane polls its own slot, the warp leaves the loop together.  (A per-lane
+// spin loop leaves the warp diverged under independent thread scheduling; every later __shfl_sync
+// then takes the divergent slow path -- measured 5x slower steps on B200.)
+// need: this lane has a slot to wait for.  Returns the entry value (undefined if !need).
+template <class Ctx>
+SWB_HD uint32_t wait_entry(const EngineParams& P, const Ctx& w, bool need, const uint2* slot, uint32_t want_tag, uint2 e,
+                           Waiter& wt) {
+  // e: what a speculative load of *slot returned one chunk ago (usually already the wanted entry)
+  for (;;) {
+    const bool ok = !need || e.y == want_tag;
+    if (w.all(ok) || wt.aborted) break;
+    bool give_up = --wt.budget < 0;
+    if ((wt.budget & 255) == 0) give_up = give_up || (ld_flag(P.result + 1) & STATUS_SPIN_TIMEOUT);
+    if (w.any(give_up)) {
+      if (!ok) record_timeout(P, 1, (long long)want_tag, (long long)e.y, (long long)e.x, wt.budget);
       atomic_or_i32(P.result + 1, STATUS_SPIN_TIMEOUT);
       wt.aborted = true;
       break;
     }
     spin_pause();
-    e = ld_entry(slot);
+    if (!ok) e = ld_entry(slot);
   }
   return e.x;
+}
+
+// Warp-uniform back-pressure wait on a monotonic progress word.
+template <class Ctx>
+SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned long long* word, unsigned long long need,
+                          long long band, long long i0, Waiter& wt) {
+  for (;;) {
+    const unsigned long long have = ld_progress(word);
+    if (w.any(have >= need) || wt.aborted) break;
+    if (w.any(--wt.budget < 0)) {
+      record_timeout(P, 2, band, i0, (long long)need, (long long)have);
+      atomic_or_i32(P.result + 1, STATUS_SPIN_TIMEOUT);
+      wt.aborted = true;
+      break;
+    }
+    spin_pause();
+  }
 }
 
 // =================================================================================================
@@ -117,9 +159,9 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   Waiter wt{P.spin_limit, false};
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
-    const bool zero_src = band == 0;
+    const bool zero_src = band == 0 || (P.dbg & 2);
     const bool has_sink = band + 1 < P.NB;
-    const bool emit = has_sink && last_lane;
+    const bool emit = has_sink && last_lane && !(P.dbg & 1);
     const bool first_local = lw == 0, last_local = lw == P.warps_local - 1;
     const uint2* in = first_local ? P.ext_in : P.links + (size_t)(lw - 1) * 2 * ((size_t)P.link_mask + 1);
     const unsigned in_mask = first_local ? P.ext_mask : P.link_mask;
@@ -131,6 +173,11 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     const uint32_t out_tag = P.tag_base | ((uint32_t)(band + 1) << 8);
     unsigned long long* my_progress = P.progress + lw;
     const unsigned long long* sink_progress = P.progress + lw + 1;       // only read when !last_local
+    // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a
+    // ring is one continuous stream and back-pressure spans band boundaries; the full-length ext
+    // stream restarts at 0 every band (safe: see DESIGN.md, hand-off protocol).
+    const long long sbase = (band / P.ring_total) * nsteps;
+    const long long in_base = first_local ? 0 : sbase, out_base = last_local ? 0 : sbase;
 
     // ---- per-band constants: PRMT selectors of this thread's 2*R rows
     uint32_t sel[R];
@@ -163,50 +210,66 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       sm->tab[q & (kTabRing - 1)] = tw;
       sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
     }
+    // ---- loads issued one chunk ahead of their use: the packed T word of positions [32,64) and a
+    //      speculative read of this lane's first boundary entry
+    uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(P.t_packed + ((kChunk + lane) >> 5)) : 0ull;
+    uint2 epref = make_uint2(0u, 0u);
+    if (!zero_src && SLACK + lane < LT) epref = ld_entry(in + ((in_base + SLACK + lane + SKEW) & in_mask));
 
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
-      // (a) substitution tables for T positions [i0+32, i0+64)
+#if SWB_DEVICE_CODE
+      const long long tp0 = P.prof ? clock64() : 0;
+      const long long bud0 = wt.budget;
+#endif
+      // (a) substitution tables for T positions [i0+32, i0+64); fetch the word after that
       {
         const long long q = i0 + kChunk + lane;
         uint32_t c = 4;
-        if (q < LT) c = (uint32_t)(P.t_packed[q >> 5] >> (2 * (q & 31))) & 3u;
+        if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
         const uint32_t tw = table_word(c, padw, flip);
         sm->tab[q & (kTabRing - 1)] = tw;
         sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
+        twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
       }
       // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): wait for the producer
       {
         const long long q = i0 + SLACK + lane;
         uint32_t v = nopen;
-        if (!zero_src && q < LT) {
-          const long long j = q + SKEW;                                   // producer step that emitted q
-          v = wait_entry(P, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), wt);
+        if (!zero_src) {                                                  // warp-uniform branch
+          const bool need = q < LT;
+          const long long j = in_base + q + SKEW;                         // producer step that emitted q
+          const uint32_t got =
+              wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
+          if (need) v = got;
+          if (q + kChunk < LT) epref = ld_entry(in + ((j + kChunk) & in_mask));   // next chunk, speculative
         }
         sm->inbox[q & (kInbox - 1)] = v;
         sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
         if (lane == 0 && (i0 & 255) == 0)
-          st_progress(my_progress, ((unsigned long long)(band + 1) << 32) | (unsigned long long)(i0 + SLACK + kChunk));
+          st_progress(my_progress, (unsigned long long)(sbase + i0 + SLACK + kChunk));
       }
       // (c) ring back-pressure: never overwrite an entry the consumer has not read yet
-      if (has_sink && !last_local && (i0 & 1023) == 0 && i0 + 1024 > (long long)out_mask + 1) {
-        const unsigned long long need =
-            ((unsigned long long)(band + 2) << 32) | (unsigned long long)(i0 + 1024 - ((long long)out_mask + 1));
-        while (!wt.aborted && ld_progress(sink_progress) < need) {
-          if (--wt.budget < 0) { atomic_or_i32(P.result + 1, STATUS_SPIN_TIMEOUT); wt.aborted = true; }
-          spin_pause();
-        }
+      if (has_sink && !last_local && ((sbase + i0) & 1023) == 0 && sbase + i0 + 1024 > (long long)out_mask + 1) {
+        const unsigned long long need = (unsigned long long)(sbase + i0 + 1024 - ((long long)out_mask + 1));
+        wait_progress(P, w, sink_progress, need, band, i0, wt);
       }
       w.sync();
+#if SWB_DEVICE_CODE
+      const long long tp1 = P.prof ? clock64() : 0;
+#endif
 
       const uint32_t* tabp = sm->tab + ((i0 - (long long)SK * lane) & (kTabRing - 1));
       const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
-      uint2* outp = out + (i0 & out_mask);
-      const uint32_t otag = out_tag | ((uint32_t)(i0 >> out_shift) & 0xFFu);
+      uint2* outp = out + ((out_base + i0) & out_mask);
+      const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
 
+      uint32_t Tnext = tabp[0], xnext = inbp[0];       // loaded one step ahead of use
 #pragma unroll 4
       for (int k = 0; k < kChunk; ++k) {
-        const uint32_t Tlo = tabp[k];
-        const uint32_t xin = inbp[k];
+        const uint32_t Tlo = Tnext;
+        const uint32_t xin = xnext;
+        Tnext = tabp[k + 1];
+        xnext = inbp[k + 1];
         const uint32_t xs = last_lane ? xin : xsend;
         const uint32_t ynew = w.shfl(xs, src_lane);
         const uint32_t yuse = SLACK ? yold : ynew;
@@ -245,7 +308,16 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         // slot = producer step (always in range); steps whose T position is outside [0,LT) are never read
         if (emit) st_entry(outp + k, xsend, otag);
       }
+#if SWB_DEVICE_CODE
+      if (P.prof) {
+        const long long tp2 = clock64();
+        long long* pr = P.prof + 4 * lw;
+        if (lane == 31) { pr[0] += tp1 - tp0; pr[1] += tp2 - tp1; pr[3] += 1; }
+        if (lane == 31) pr[2] += bud0 - wt.budget;
+      }
+#endif
     }
+    if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + nsteps));
   }
 
   // ---- running best: halves -> int, warp max, one atomic
@@ -279,9 +351,9 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
   Waiter wt{P.spin_limit, false};
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
-    const bool zero_src = band == 0;
+    const bool zero_src = band == 0 || (P.dbg & 2);
     const bool has_sink = band + 1 < P.NB;
-    const bool emit = has_sink && last_lane;
+    const bool emit = has_sink && last_lane && !(P.dbg & 1);
     const bool first_local = lw == 0, last_local = lw == P.warps_local - 1;
     const uint2* in = first_local ? P.ext_in : P.links + (size_t)(lw - 1) * 2 * ((size_t)P.link_mask + 1);
     const unsigned in_mask = first_local ? P.ext_mask : P.link_mask;
@@ -293,6 +365,11 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     const uint32_t out_tag = P.tag_base | ((uint32_t)(band + 1) << 8);
     unsigned long long* my_progress = P.progress + lw;
     const unsigned long long* sink_progress = P.progress + lw + 1;
+    // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a
+    // ring is one continuous stream and back-pressure spans band boundaries; the full-length ext
+    // stream restarts at 0 every band (safe: see DESIGN.md, hand-off protocol).
+    const long long sbase = (band / P.ring_total) * nsteps;
+    const long long in_base = first_local ? 0 : sbase, out_base = last_local ? 0 : sbase;
 
     uint32_t sel[R];
     {
@@ -320,51 +397,65 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       sm->tab[q & (kTabRing - 1)] = tw;
       sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
     }
+    uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(P.t_packed + ((kChunk + lane) >> 5)) : 0ull;
+    uint2 eprefH = make_uint2(0u, 0u), eprefF = make_uint2(0u, 0u);
+    if (!zero_src && SLACK + lane < LT) {
+      eprefH = ld_entry(in + 2 * ((in_base + SLACK + lane + SKEW) & in_mask));
+      eprefF = ld_entry(in + 2 * ((in_base + SLACK + lane + SKEW) & in_mask) + 1);
+    }
 
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
       {
         const long long q = i0 + kChunk + lane;
         uint32_t c = 4;
-        if (q < LT) c = (uint32_t)(P.t_packed[q >> 5] >> (2 * (q & 31))) & 3u;
+        if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
         const uint32_t tw = table_word(c, padw, flip);
         sm->tab[q & (kTabRing - 1)] = tw;
         sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
+        twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
       }
       {
         const long long q = i0 + SLACK + lane;
         uint32_t vH = (uint32_t)nopen, vF = (uint32_t)nopen;
-        if (!zero_src && q < LT) {
-          const long long j = q + SKEW;
+        if (!zero_src) {
+          const bool need = q < LT;
+          const long long j = in_base + q + SKEW;
           const uint32_t tg = in_tag | ((uint32_t)(j >> in_shift) & 0xFFu);
-          vH = wait_entry(P, in + 2 * (j & in_mask), tg, wt);
-          vF = wait_entry(P, in + 2 * (j & in_mask) + 1, tg, wt);
+          const uint32_t gH = wait_entry(P, w, need, in + 2 * (j & in_mask), tg, eprefH, wt);
+          const uint32_t gF = wait_entry(P, w, need, in + 2 * (j & in_mask) + 1, tg, eprefF, wt);
+          if (need) { vH = gH; vF = gF; }
+          if (q + kChunk < LT) {
+            eprefH = ld_entry(in + 2 * ((j + kChunk) & in_mask));
+            eprefF = ld_entry(in + 2 * ((j + kChunk) & in_mask) + 1);
+          }
         }
         sm->inbox[q & (kInbox - 1)] = vH;
         sm->inbox[(q & (kInbox - 1)) + kInbox] = vH;
         sm->inbox[(q & (kInbox - 1)) + 2 * kInbox] = vF;
         sm->inbox[(q & (kInbox - 1)) + 3 * kInbox] = vF;
         if (lane == 0 && (i0 & 255) == 0)
-          st_progress(my_progress, ((unsigned long long)(band + 1) << 32) | (unsigned long long)(i0 + SLACK + kChunk));
+          st_progress(my_progress, (unsigned long long)(sbase + i0 + SLACK + kChunk));
       }
-      if (has_sink && !last_local && (i0 & 1023) == 0 && i0 + 1024 > (long long)out_mask + 1) {
-        const unsigned long long need =
-            ((unsigned long long)(band + 2) << 32) | (unsigned long long)(i0 + 1024 - ((long long)out_mask + 1));
-        while (!wt.aborted && ld_progress(sink_progress) < need) {
-          if (--wt.budget < 0) { atomic_or_i32(P.result + 1, STATUS_SPIN_TIMEOUT); wt.aborted = true; }
-          spin_pause();
-        }
+      if (has_sink && !last_local && ((sbase + i0) & 1023) == 0 && sbase + i0 + 1024 > (long long)out_mask + 1) {
+        const unsigned long long need = (unsigned long long)(sbase + i0 + 1024 - ((long long)out_mask + 1));
+        wait_progress(P, w, sink_progress, need, band, i0, wt);
       }
       w.sync();
 
       const uint32_t* tabp = sm->tab + ((i0 - (long long)SK * lane) & (kTabRing - 1));
       const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
-      uint2* outp = out + 2 * (i0 & out_mask);
-      const uint32_t otag = out_tag | ((uint32_t)(i0 >> out_shift) & 0xFFu);
+      uint2* outp = out + 2 * ((out_base + i0) & out_mask);
+      const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
 
+      uint32_t Tnext = tabp[0];
+      int xnH = (int)inbp[0], xnF = (int)inbp[2 * kInbox];
 #pragma unroll 4
       for (int k = 0; k < kChunk; ++k) {
-        const uint32_t Tw = tabp[k];
-        const int xinH = (int)inbp[k], xinF = (int)inbp[k + 2 * kInbox];
+        const uint32_t Tw = Tnext;
+        const int xinH = xnH, xinF = xnF;
+        Tnext = tabp[k + 1];
+        xnH = (int)inbp[k + 1];
+        xnF = (int)inbp[k + 1 + 2 * kInbox];
         const int ynewH = (int)w.shfl((uint32_t)(last_lane ? xinH : xsH), src_lane);
         const int ynewF = (int)w.shfl((uint32_t)(last_lane ? xinF : xsF), src_lane);
         const int upHo = SLACK ? yoldH : ynewH;
@@ -393,6 +484,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
         }
       }
     }
+    if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + nsteps));
   }
   int m = w.reduce_max(best0 > best1 ? best0 : best1);
   if (lane == 0) atomic_max_i32(P.result, m);

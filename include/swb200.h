@@ -43,7 +43,8 @@ typedef struct {
   int config;      /* 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA) */
   int ctas;        /* thread blocks (<= co-resident limit); 0 auto */
   int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
-  int reserved[3];
+  int orient;      /* 0 auto (stripe the longer sequence across lanes), 1 = stripe seq1, 2 = stripe seq2 */
+  int reserved[2];
 } swb200_options;
 
 /* Return codes (legacy names have no error channel: they print and abort instead). */
