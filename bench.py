@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

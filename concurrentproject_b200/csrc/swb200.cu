@@ -164,23 +164,26 @@ struct Plan {
   bool swap;     // Q = seq2 instead of seq1
 };
 
-// Estimated cycles for one (R, config) choice: steps the slowest warp executes times cycles per step.
-// The constants come from bench/intpeak.cu and the first B200 sweeps (profiles/); they only steer the
-// choice, never the result.
+// Estimated cycles for one (R, config) choice.  Model and constants fitted to B200 sweeps
+// (profiles/r01_sweep_*.jsonl): a warp-step costs per_row*R + 39 cycles with one warp per scheduler
+// (14 / 10 / 12.5 cycles per row vector for s16 affine / s16 linear / s32), 1.5x that per warp when two
+// warps share a scheduler; a band starts `lag` steps after the band above it (lane skew + 64 steps of
+// poll look-ahead + ~60 steps of L2 visibility); the pair is done when the last band is.
+// The estimate only steers the choice of kernel, never the result.
 double estimate(long long LQ, long long LT, int mode, int R, int config, int sms) {
   const int rpb = swb::rows_per_band(R, mode);
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
-  const long long rounds = (NB + W - 1) / W;
-  const long long active = std::min<long long>(NB, W);
   const int skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const double per_row = mode == 1 ? 5.0 : 7.0;
-  const double instr = per_row * R + 12.0;                       // issue slots per step per warp
-  const double cyc_step = config == 1 ? std::max(instr * 1.25, 8.0 * R + 30.0)  // one warp per scheduler
-                                      : instr * 2.2;                             // two warps share a scheduler
-  const double steps = (double)rounds * (double)(LT + skew) + (double)active * (skew + 32 + 48);
-  return steps * cyc_step;
+  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : 12.5);
+  double cyc_step = per_row * R + 39.0;
+  if (config == 2) cyc_step *= 1.5;
+  if (config == 3) cyc_step += std::max(0.0, 30.0 - (mode == 1 ? 4.0 : 6.0) * R);   // exposed SHFL latency
+  const double lag = skew + 64 + 60;
+  const long long b = NB - 1, w = b % W, r = b / W;
+  const double start = std::max((double)w * lag + (double)r * (double)(LT + skew), (double)b * lag);
+  return (start + (double)(LT + skew)) * cyc_step;
 }
 
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms) {

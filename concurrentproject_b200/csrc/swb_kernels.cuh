@@ -6,8 +6,10 @@ namespace swb {
 
 // config 1: 4 warps per CTA (one per SM scheduler), boundary value consumed one step late (SLACK 1)
 // config 2: 8 warps per CTA (two per scheduler), consumed in the same step (SLACK 0)
-constexpr int kNumConfigs = 2;
-SWB_HD int config_wpc(int config) { return config == 1 ? 4 : 8; }
+// config 3: 4 warps per CTA, consumed in the same step (shortest pipeline; the SHFL latency is covered by
+//           the independent E / substitution work once R is large enough)
+constexpr int kNumConfigs = 3;
+SWB_HD int config_wpc(int config) { return config == 2 ? 8 : 4; }
 SWB_HD int config_slack(int config) { return config == 1 ? 1 : 0; }
 
 constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 12, 16};
@@ -34,7 +36,8 @@ static const void* engine_kernel_lookup(int R, int config) {
 #define SWB_CASE(RR)                                                             \
   case RR:                                                                       \
     return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
-                       : (const void*)sw_engine_kernel<RR, MODE, 0, 8>;
+         : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \
+                       : (const void*)sw_engine_kernel<RR, MODE, 0, 4>;
   switch (R) {
     SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16)
     default: return nullptr;
