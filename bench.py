@@ -45,7 +45,12 @@ WORKLOADS = {
     "cfg1": (1000, 1000, 1, "10 pairs 1000x1000 (TestFile.cpp default)"),
     "cfg2": (100000, 100000, 2, "single pair 100000x100000, seed 2, MATCH=1 MISMATCH=-1 GAP_INIT=1 GAP_EXT=1"),
     "n1m": (1000000, 1000000, 6, "single pair 1000000x1000000, seed 6"),
+    # one pair spread over the ring of all GPUs (strong scaling): boundary stream pushed GPU to GPU over NVLink
+    "ring400k": (400000, 400000, 7, "single pair 400000x400000, seed 7, DP bands cyclically striped over all GPUs"),
+    "ring1m": (1000000, 1000000, 6, "single pair 1000000x1000000, seed 6, DP bands cyclically striped over all GPUs"),
+    "cfg3": (4000000, 4000000, 3, "single pair 4000000x4000000, seed 3, DP bands cyclically striped over all GPUs"),
 }
+RING_WORKLOADS = {"ring400k", "ring1m", "cfg3"}
 
 
 def golden_score(name):
@@ -158,6 +163,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, m, seed, desc = WORKLOADS[args.workload]
+    if args.workload in RING_WORKLOADS:
+        return run_ring(args, torch, dist, api, world, rank, local)
     # weak scaling over pairs: rank r scores its own pair (streams 2r, 2r+1); no data-path collective
     a_h = rng.random_acgt(seed, 2 * rank, n)
     b_h = rng.random_acgt(seed, 2 * rank + 1, m)
@@ -245,6 +252,64 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_ring(args, torch, dist, api, world, rank, local):
+    """One long pair over all GPUs (strong scaling).  Every rank holds both sequences; the DP bands are dealt
+    cyclically to the warps of all GPUs and the boundary stream crosses GPUs inside the kernel."""
+    from concurrentproject_b200.ring import DistributedRingAligner
+    if world == 1:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29591", rank=0, world_size=1,
+                                device_id=torch.device("cuda", local))
+    n, m, seed, desc = WORKLOADS[args.workload]
+    a_h = rng.random_acgt(seed, 0, n)
+    b_h = rng.random_acgt(seed, 1, m)
+    a_d = torch.from_numpy(a_h.copy()).cuda()
+    b_d = torch.from_numpy(b_h.copy()).cuda()
+    al = DistributedRingAligner(local, min(n, m))
+    stream = torch.cuda.current_stream()
+    lanes = 32 if min(n, m) > 250000 else 0       # random DNA scores ~0.114*N: skip the 16-bit attempt when it cannot fit
+    scores = []
+    for _ in range(max(args.warmup, 1)):
+        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kms = []
+    for _ in range(args.steps):
+        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
+        kms.append(al.last_run()["engine_ms"])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    assert len(set(scores)) == 1, scores
+    cells = float(n) * float(m)
+    if rank == 0:
+        info = al.last_run()
+        value = cells * args.steps / (ms * 1e-3) / 1e9
+        f_mhz = clocks["sm_mhz"] or 1965
+        vwidth = 2 if info["lanes"] == 16 else 1
+        peak = world * N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 1), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "s16x2" if info["lanes"] == 16 else "s32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": desc, "l2": "working set is registers; boundary rings stream through L2",
+                           "kernel": info, "score": scores[-1]},
+                "clocks": clocks, "gpu_launches": 3 * args.steps,
+                "e2e": None,
+                "roofline": {"bound": "int_alu", "achieved": round(value, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                             "frac": round(value / peak, 4), "traffic": None,
+                             "note": f"whole ring of {world} GPU(s); peak = {world} x 148 SM x {f_mhz} MHz x L=64 x V={vwidth} / 7"}}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    al.close()
+    dist.destroy_process_group()
 
 
 def main():

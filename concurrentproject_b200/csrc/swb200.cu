@@ -136,6 +136,16 @@ struct swb200_ctx {
   swb200_run_info info{};
 };
 
+struct swb200_ring {
+  swb200_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  uint2* inbound = nullptr;
+  size_t entries = 0;
+  uint2* next = nullptr;
+  bool next_is_ipc = false;
+  unsigned calls = 0;
+};
+
 namespace {
 
 template <typename T>
@@ -216,11 +226,21 @@ const void* kernel_for(const Plan& pl) {
 
 int log2_ceil(long long v) { int s = 0; while ((1LL << s) < v) ++s; return s; }
 
+// Present when the pair is spread over a ring of GPUs (one swb200_ring per rank).
+struct RingCfg {
+  int rank, world;
+  uint2* inbound;        // this rank's boundary stream buffer (consumed by local warp 0)
+  uint2* next_inbound;   // the next rank's buffer, mapped into this process (peer stores over NVLink)
+  size_t inbound_entries;
+  unsigned call_epoch;   // 1..16383, identical on all ranks for one collective call
+};
+
 // Encode + one engine run at a fixed lane width.  d_seq1/d_seq2 are device pointers.
 int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
              const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
-             int* score, int* status) {
-  const Plan pl = make_plan(n, m, p, o, lanes, c->sms);
+             int* score, int* status, const RingCfg* ring = nullptr) {
+  const int world = ring ? ring->world : 1;
+  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world);
   const void* kern = kernel_for(pl);
   if (!kern) return fail(SWB200_ERR_ARG, "no kernel for rows=" + std::to_string(pl.R));
   const uint8_t* dq = pl.swap ? d_seq2 : d_seq1;
@@ -230,6 +250,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int rpb = swb::rows_per_band(pl.R, pl.mode);
   const long long NB = (LQ + rpb - 1) / rpb;
   if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
+  if (ring && NB > 1 && ring->call_epoch == 0) return fail(SWB200_ERR_ARG, "ring epoch exhausted; create a new ring");
 
   int per_sm = 0;
   SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, 0));
@@ -237,6 +258,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   long long ctas = std::min<long long>((NB + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
   if (pl.ctas > 0) ctas = std::min<long long>(ctas, pl.ctas);
   ctas = std::max<long long>(ctas, 1);
+  if (ring) ctas = pl.ctas > 0 ? std::min<long long>(pl.ctas, c->sms) : c->sms;   // every rank launches the same shape
   const int warps = (int)ctas * wpc;
 
   const int skew = pl.mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
@@ -254,7 +276,10 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const size_t ext_need = 2 * (size_t)ext_len;
   const bool links_fresh = links_need > c->links_cap, ext_fresh = ext_need > c->ext_cap;
   if ((rc = grow(c->d_links, c->links_cap, links_need, true, s))) return rc;
-  if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
+  if (ring) {
+    if (ext_need > ring->inbound_entries)
+      return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
+  } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
   if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 2, false, s))) return rc;
   (void)links_fresh; (void)ext_fresh;
 
@@ -263,7 +288,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   if (c->epoch > 63) {
     c->epoch = 1;
     SWB_CUDA(cudaMemsetAsync(c->d_links, 0, c->links_cap * sizeof(uint2), s));
-    SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
+    if (c->d_ext) SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
   }
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 2) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
@@ -277,11 +302,13 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
 
   swb::EngineParams P{};
   P.q_codes = c->d_q; P.t_packed = c->d_t; P.LQ = LQ; P.LT = LT; P.NB = (int)NB;
-  P.ring_total = warps; P.ring_offset = 0; P.warps_local = warps;
+  P.ring_total = warps * world; P.ring_offset = ring ? ring->rank * warps : 0; P.warps_local = warps;
   P.links = c->d_links; P.link_mask = (unsigned)(link_len - 1); P.link_shift = link_shift;
   P.progress = c->d_progress;
-  P.ext_in = c->d_ext; P.ext_out = c->d_ext; P.ext_mask = (unsigned)(ext_len - 1); P.ext_shift = ext_shift;
+  P.ext_in = ring ? ring->inbound : c->d_ext; P.ext_out = ring ? ring->next_inbound : c->d_ext;
+  P.ext_mask = (unsigned)(ext_len - 1); P.ext_shift = ext_shift;
   P.tag_base = c->epoch << 26; P.result = c->d_result;
+  P.ext_tag_base = ring ? (((ring->call_epoch >> 8) & 0x3Fu) << 26) | (ring->call_epoch & 0xFFu) : P.tag_base;
   P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
   P.spin_limit = getenv("SWB200_SPIN_LIMIT") ? atoll(getenv("SWB200_SPIN_LIMIT")) : 40LL * 1000 * 1000;
   P.dbg = getenv("SWB200_DBG") ? atoi(getenv("SWB200_DBG")) : 0;
@@ -505,6 +532,84 @@ int swb200_last_run(swb200_ctx* c, swb200_run_info* info) {
   std::lock_guard<std::mutex> lk(c->mu);
   *info = c->info;
   return SWB200_OK;
+}
+
+// ---- one pair over a ring of GPUs (one swb200_ring per GPU / per process) -------------------------
+int swb200_ring_create(swb200_ctx* c, int rank, int world, long long max_stream_len, swb200_ring** ring_out,
+                       unsigned char handle_out[64]) {
+  if (!c || !ring_out || !handle_out || world < 1 || rank < 0 || rank >= world || max_stream_len < 1)
+    return fail(SWB200_ERR_ARG, "bad ring arguments");
+  std::lock_guard<std::mutex> lk(c->mu);
+  SWB_CUDA(cudaSetDevice(c->device));
+  swb200_ring* r = new swb200_ring();
+  r->ctx = c; r->rank = rank; r->world = world;
+  const long long len = 1LL << log2_ceil(max_stream_len + 4 * 96 + 2 * swb::kChunk);
+  r->entries = 2 * (size_t)len;
+  SWB_CUDA(cudaMalloc(&r->inbound, r->entries * sizeof(uint2)));
+  SWB_CUDA(cudaMemset(r->inbound, 0, r->entries * sizeof(uint2)));
+  cudaIpcMemHandle_t h;
+  SWB_CUDA(cudaIpcGetMemHandle(&h, r->inbound));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle_out, &h, 64);
+  *ring_out = r;
+  return SWB200_OK;
+}
+
+int swb200_ring_connect(swb200_ring* r, const unsigned char next_handle[64]) {
+  if (!r || !next_handle) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  std::lock_guard<std::mutex> lk(r->ctx->mu);
+  SWB_CUDA(cudaSetDevice(r->ctx->device));
+  if (r->world == 1) { r->next = r->inbound; return SWB200_OK; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, next_handle, 64);
+  void* p = nullptr;
+  SWB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  r->next = reinterpret_cast<uint2*>(p);
+  r->next_is_ipc = true;
+  return SWB200_OK;
+}
+
+int swb200_ring_connect_local(swb200_ring* r, swb200_ring* next) {
+  if (!r || !next) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  if (next->entries != r->entries) return fail(SWB200_ERR_ARG, "rings of different capacity");
+  if (next->ctx->device != r->ctx->device) {
+    SWB_CUDA(cudaSetDevice(r->ctx->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(next->ctx->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(SWB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  r->next = next->inbound;
+  return SWB200_OK;
+}
+
+int swb200_ring_score_device(swb200_ring* r, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2,
+                             long long m, const swb200_params* pp, const swb200_options* oo, void* stream,
+                             int* partial_score_out, int* status_out) {
+  if (!r || !partial_score_out || !status_out) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  if (!r->next) return fail(SWB200_ERR_ARG, "ring is not connected");
+  swb200_ctx* c = r->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  swb200_options o = oo ? *oo : swb200_options{};
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  if (n < 1 || m < 1) return fail(SWB200_ERR_ARG, "ring scoring needs non-empty sequences");
+  if (o.lanes != 16 && o.lanes != 32) return fail(SWB200_ERR_ARG, "ring scoring needs an explicit lane width (16 or 32)");
+  SWB_CUDA(cudaSetDevice(c->device));
+  c->info = swb200_run_info{};
+  c->info.cells = n * m;
+  r->calls += 1;
+  RingCfg cfg{r->rank, r->world, r->inbound, r->next, r->entries, r->calls < 16384 ? r->calls : 0u};
+  return run_once(c, d_seq1, n, d_seq2, m, p, o, o.lanes, nullptr, (cudaStream_t)stream, partial_score_out, status_out, &cfg);
+}
+
+void swb200_ring_destroy(swb200_ring* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  if (r->next_is_ipc && r->next) cudaIpcCloseMemHandle(r->next);
+  cudaFree(r->inbound);
+  delete r;
 }
 
 // ---- the reference's names (algoGPU.h:5-9, SmithDiagonalGPUrefactored.cu:174) ---------------------

@@ -48,7 +48,8 @@ struct EngineParams {
   uint2* ext_out;               // stream produced by the last local warp (peer memory on multi-GPU)
   unsigned ext_mask;
   int ext_shift;
-  uint32_t tag_base;            // epoch << 26
+  uint32_t tag_base;            // local rings: epoch << 26
+  uint32_t ext_tag_base;        // ext streams: 14-bit call epoch, high 6 bits << 26 | low 8 bits (ext lap bits are always 0)
   int* result;                  // [0] best score (atomicMax), [1] status bits (atomicOr)
   int match, mismatch, gap_init, gap_ext;
   long long spin_limit;         // polls before a waiting warp gives up (sets STATUS_SPIN_TIMEOUT)
@@ -169,8 +170,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     uint2* out = last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1);
     const unsigned out_mask = last_local ? P.ext_mask : P.link_mask;
     const int out_shift = last_local ? P.ext_shift : P.link_shift;
-    const uint32_t in_tag = P.tag_base | ((uint32_t)band << 8);           // written by band-1 as (band-1)+1
-    const uint32_t out_tag = P.tag_base | ((uint32_t)(band + 1) << 8);
+    const uint32_t in_tag = (first_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)band << 8);   // written by band-1 as (band-1)+1
+    const uint32_t out_tag = (last_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)(band + 1) << 8);
     unsigned long long* my_progress = P.progress + lw;
     const unsigned long long* sink_progress = P.progress + lw + 1;       // only read when !last_local
     // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a
@@ -361,8 +362,8 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     uint2* out = last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1);
     const unsigned out_mask = last_local ? P.ext_mask : P.link_mask;
     const int out_shift = last_local ? P.ext_shift : P.link_shift;
-    const uint32_t in_tag = P.tag_base | ((uint32_t)band << 8);
-    const uint32_t out_tag = P.tag_base | ((uint32_t)(band + 1) << 8);
+    const uint32_t in_tag = (first_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)band << 8);
+    const uint32_t out_tag = (last_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)(band + 1) << 8);
     unsigned long long* my_progress = P.progress + lw;
     const unsigned long long* sink_progress = P.progress + lw + 1;
     // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a

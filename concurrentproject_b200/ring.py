@@ -1,0 +1,98 @@
+"""One very long pair spread over a ring of GPUs, one process per GPU (BASELINE config 3).
+
+Host-side orchestration only: the boundary hand-off between GPUs happens inside the wavefront kernel
+(peer stores into the next GPU's memory, include/swb200.h "ring").  torch.distributed is used for the
+plumbing the C ABI leaves to the caller: exchanging the 64-byte CUDA IPC handles once, and the final
+max over the ranks' partial scores (one 3-int all-reduce per call; no data-path collective)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+from . import _lib
+from .api import DEFAULT_PARAMS, Context, SwbError, _options, _params
+
+STATUS_S16_OVERFLOW, STATUS_TIMEOUT = 1, 2
+
+
+class Ring:
+    """One rank's end of the ring.  `exchange(handle_bytes) -> list[bytes]` is any all-gather of the
+    64-byte handles (torch.distributed.all_gather_object by default)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, max_stream_len: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.handle = C.c_void_p()
+        self.ipc = (C.c_char * 64)()
+        rc = _lib.load().swb200_ring_create(ctx.handle, rank, world, max_stream_len, C.byref(self.handle), self.ipc)
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_create")
+
+    def connect_ipc(self, next_handle: bytes):
+        buf = (C.c_char * 64).from_buffer_copy(next_handle)
+        rc = _lib.load().swb200_ring_connect(self.handle, buf)
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_connect")
+
+    def connect_local(self, nxt: "Ring"):
+        rc = _lib.load().swb200_ring_connect_local(self.handle, nxt.handle)
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_connect_local")
+
+    def partial(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int,
+                stream: int = 0, rows: int = 0, config: int = 0, ctas: int = 0, no_linear: bool = False):
+        """This rank's share of one collective call: (partial best score, status bits)."""
+        score, status = C.c_int(0), C.c_int(0)
+        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear)
+        rc = _lib.load().swb200_ring_score_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
+                                                  C.byref(o), C.c_void_p(stream), C.byref(score), C.byref(status))
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_score_device")
+        return score.value, status.value
+
+    def close(self):
+        if self.handle:
+            _lib.load().swb200_ring_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class DistributedRingAligner:
+    """torch.distributed front end: rank r of the default (or given) process group drives GPU `device`."""
+
+    def __init__(self, device: int, max_stream_len: int, group=None, _ctx_factory=Context, _ring_factory=Ring):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        # the 3-int reduction travels on whatever the process group runs on (NCCL: the GPU; gloo in CPU tests: host)
+        self.reduce_device = f"cuda:{device}" if dist.get_backend(group) == "nccl" else "cpu"
+        self.ctx = _ctx_factory(device)
+        self.ring = _ring_factory(self.ctx, self.rank, self.world, max_stream_len)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(self.ring.ipc.raw), group=group)
+        self.ring.connect_ipc(handles[(self.rank + 1) % self.world]) if self.world > 1 else self.ring.connect_local(self.ring)
+        dist.barrier(group=group)
+
+    def score(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0,
+              stream: int = 0, **opts) -> int:
+        torch, dist = self.torch, self.dist
+        for width in ((16, 32) if lanes == 0 else (lanes,)):
+            part, status = self.ring.partial(d_seq1, n, d_seq2, m, params, lanes=width, stream=stream, **opts)
+            t = torch.tensor([part, status & STATUS_S16_OVERFLOW, status & STATUS_TIMEOUT], dtype=torch.int32,
+                             device=self.reduce_device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            best, overflow, timeout = (int(x) for x in t.tolist())
+            if timeout:
+                raise RuntimeError("ring hand-off timed out on some rank")
+            if not overflow:
+                return best
+            if lanes == 16:
+                raise RuntimeError("score leaves the 16-bit lane range")
+        raise RuntimeError("unreachable")
+
+    def last_run(self) -> dict:
+        return self.ctx.last_run()
+
+    def close(self):
+        self.ring.close()
+        self.ctx.close()

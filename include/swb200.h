@@ -93,6 +93,31 @@ typedef struct {
 } swb200_run_info;
 SWB200_API int swb200_last_run(swb200_ctx* ctx, swb200_run_info* info);
 
+/* ---- one very long pair over a ring of GPUs ------------------------------------------------------
+ * All warps of all GPUs form one ring of DP bands: the last warp of GPU g pushes its
+ * boundary stream straight into GPU g+1's memory (peer stores over NVLink), so neighbouring GPUs
+ * are pipelined at single-entry granularity.  One swb200_ring per GPU; with one process per GPU the
+ * 64-byte handles travel over any side channel (torch.distributed all_gather in ring.py).
+ *   create   allocates this rank's inbound boundary buffer for streamed sequences up to
+ *            max_stream_len (the shorter of the two sequences) and returns its CUDA IPC handle
+ *   connect  maps the NEXT rank's buffer ((rank+1) % world); connect_local does the same for rings
+ *            that live in this process (single-process multi-GPU, tests)
+ *   score    collective: every rank passes the same two device-resident sequences and the same
+ *            parameters/options (options.lanes must be 16 or 32); returns THIS rank's partial
+ *            best score and the raw status bits (1 = left the s16 range, 2 = hand-off timed out).
+ *            The pair's score is the max over ranks; if any rank reports bit 1, repeat with lanes=32.
+ * A ring serves 16383 calls. */
+typedef struct swb200_ring swb200_ring;
+SWB200_API int swb200_ring_create(swb200_ctx* ctx, int rank, int world, long long max_stream_len,
+                                  swb200_ring** ring_out, unsigned char handle_out[64]);
+SWB200_API int swb200_ring_connect(swb200_ring* ring, const unsigned char next_handle[64]);
+SWB200_API int swb200_ring_connect_local(swb200_ring* ring, swb200_ring* next);
+SWB200_API int swb200_ring_score_device(swb200_ring* ring, const unsigned char* d_seq1, long long n,
+                                        const unsigned char* d_seq2, long long m, const swb200_params* p,
+                                        const swb200_options* opt, void* stream, int* partial_score_out,
+                                        int* status_out);
+SWB200_API void swb200_ring_destroy(swb200_ring* ring);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,7 +99,7 @@ int main(int argc, char** argv) {
     p.progress = progress[g].data();
     p.ext_in = ext[g].data(); p.ext_out = ext[(g + 1) % G].data();
     p.ext_mask = (unsigned)(ext_len - 1); p.ext_shift = ext_shift;
-    p.tag_base = epoch << 26; p.result = result;
+    p.tag_base = epoch << 26; p.ext_tag_base = (epoch << 26) | 0x5Au; p.result = result;
     p.match = ma; p.mismatch = mi; p.gap_init = gi; p.gap_ext = ge;
     p.spin_limit = 200000000LL;
   }

@@ -150,3 +150,28 @@ def test_size_independent_properties_at_scale(api):
     assert api.score(b"A" * n, b"C" * n) == 0                               # disjoint alphabets -> 0
     b = np.concatenate([a[:150000], a[150007:]])                            # 7 deleted bases: one gap of 7
     assert api.score(a, b) == max(150000, (n - 7) - (1 + 6 * 1))
+
+
+def test_ring_of_virtual_ranks_on_one_gpu(api):
+    """The multi-GPU ring code path (ring offsets, ext streams as separate buffers, 14-bit call epoch)
+    with all ranks on cuda:0.  Kernels of different ranks must not wait on each other on one GPU, so
+    the pair is sized for a single round and the ranks run one after the other (rank r only needs
+    data rank r-1 has already pushed)."""
+    import torch
+    from concurrentproject_b200.ring import Ring
+    world = 3
+    a, b = planted(600, 16000, 0.08, 0.03)       # 16000 rows / (64*4) = 63 bands < 3 ranks * 148*4 warps
+    ta = torch.from_numpy(a.copy()).cuda(); tb = torch.from_numpy(b.copy()).cuda()
+    want = O.gotoh_mt(a, b)
+    ctxs = [api.Context(0) for _ in range(world)]
+    rings = [Ring(ctxs[r], r, world, len(a) + len(b)) for r in range(world)]
+    for r in range(world):
+        rings[r].connect_local(rings[(r + 1) % world])
+    for lanes, rows, ctas, cfg in ((16, 4, 6, 1), (32, 4, 12, 3), (16, 2, 11, 2)):
+        parts = [rings[r].partial(ta.data_ptr(), len(a), tb.data_ptr(), len(b), lanes=lanes, rows=rows, ctas=ctas, config=cfg,
+                                  no_linear=True) for r in range(world)]
+        assert all(st == 0 for _, st in parts), parts
+        assert max(s for s, _ in parts) == want, (parts, want)
+        assert sum(1 for s, _ in parts if s > 0) >= 2           # the work really was spread over the ranks
+    for x in rings:
+        x.close()
