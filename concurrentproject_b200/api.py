@@ -127,3 +127,70 @@ class Context:
 
     def last_run(self) -> dict:
         return last_run(self)
+
+
+def _flatten(seqs):
+    arrs = [_u8(s) for s in seqs]
+    lens = np.array([len(a) for a in arrs], dtype=np.int32)
+    offs = np.zeros(len(arrs), dtype=np.int64)
+    if len(arrs) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.int64)
+    flat = np.concatenate(arrs) if len(arrs) and int(lens.sum()) else np.zeros(1, dtype=np.uint8)
+    return np.ascontiguousarray(flat), offs, lens
+
+
+def score_batch(seqs1, seqs2, params: Sequence[int] = DEFAULT_PARAMS, *, rows: int = 0, no_linear: bool = False) -> np.ndarray:
+    """Scores of many independent HOST pairs in one kernel (swb200_score_batch).  seqs1[k] vs seqs2[k]."""
+    if len(seqs1) != len(seqs2):
+        raise ValueError("seqs1 and seqs2 differ in length")
+    f1, o1, l1 = _flatten(seqs1)
+    f2, o2, l2 = _flatten(seqs2)
+    out = np.zeros(len(seqs1), dtype=np.int32)
+    p, o = _params(params), _options(rows=rows, no_linear=no_linear)
+    LL, I = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+    rc = _lib.load().swb200_score_batch(_ptr(f1), o1.ctypes.data_as(LL), l1.ctypes.data_as(I), _ptr(f2), o2.ctypes.data_as(LL),
+                                        l2.ctypes.data_as(I), len(seqs1), C.byref(p), C.byref(o), out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_batch")
+    return out
+
+
+def score_batch_flat(flat1: np.ndarray, off1: np.ndarray, len1: np.ndarray, flat2: np.ndarray, off2: np.ndarray,
+                     len2: np.ndarray, params: Sequence[int] = DEFAULT_PARAMS, *, rows: int = 0, no_linear: bool = False) -> np.ndarray:
+    """swb200_score_batch on already flattened HOST arrays (uint8 bytes, int64 offsets, int32 lengths)."""
+    n = len(len1)
+    out = np.zeros(n, dtype=np.int32)
+    p, o = _params(params), _options(rows=rows, no_linear=no_linear)
+    LL, I = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+    rc = _lib.load().swb200_score_batch(_ptr(flat1), off1.ctypes.data_as(LL), len1.ctypes.data_as(I), _ptr(flat2),
+                                        off2.ctypes.data_as(LL), len2.ctypes.data_as(I), n, C.byref(p), C.byref(o),
+                                        out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_batch")
+    return out
+
+
+class PackedBatch:
+    """A batch packed into the HBM-resident 2-bit format (swb200_batch_*).  All arguments are device addresses."""
+
+    def __init__(self, ctx: Context, d_seq1: int, d_off1: int, d_len1: int, d_seq2: int, d_off2: int, d_len2: int, npairs: int,
+                 max_short: int, max_long: int, total_cells: int, stream: int = 0):
+        self.ctx, self.npairs = ctx, npairs
+        self.handle = C.c_void_p()
+        rc = _lib.load().swb200_batch_pack_device(ctx.handle, C.c_void_p(d_seq1), C.c_void_p(d_off1), C.c_void_p(d_len1),
+                                                  C.c_void_p(d_seq2), C.c_void_p(d_off2), C.c_void_p(d_len2), npairs, max_short,
+                                                  max_long, total_cells, C.c_void_p(stream), C.byref(self.handle))
+        if rc != 0:
+            raise SwbError(rc, "swb200_batch_pack_device")
+
+    def score(self, d_scores: int, params: Sequence[int] = DEFAULT_PARAMS, *, stream: int = 0, rows: int = 0,
+              no_linear: bool = False) -> None:
+        p, o = _params(params), _options(rows=rows, no_linear=no_linear)
+        rc = _lib.load().swb200_batch_score(self.handle, C.byref(p), C.byref(o), C.c_void_p(stream), C.c_void_p(d_scores))
+        if rc != 0:
+            raise SwbError(rc, "swb200_batch_score")
+
+    def close(self):
+        if self.handle:
+            _lib.load().swb200_batch_free(self.handle)
+            self.handle = C.c_void_p()

@@ -93,6 +93,29 @@ typedef struct {
 } swb200_run_info;
 SWB200_API int swb200_last_run(swb200_ctx* ctx, swb200_run_info* info);
 
+/* ---- batches of independent pairs (reads vs windows) ----------------------------------------------
+ * The reference scores pairs one call at a time (TestFileWithGPU.cpp:57-94); a batch call scores
+ * npairs independent pairs in one kernel, several pairs per warp, nothing leaving the registers.
+ * Pair k is seq1_all[off1[k] .. off1[k]+len1[k]) vs seq2_all[off2[k] .. off2[k]+len2[k]).
+ * Limits: bytes must be A,C,G,T; min(len1[k], len2[k]) <= 1024 and match*min(len) <= 32766 for every
+ * pair (longer pairs: swb200_score).  Empty sequences score 0. */
+SWB200_API int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                                  const unsigned char* seq2_all, const long long* off2, const int* len2,
+                                  long long npairs, const swb200_params* p, const swb200_options* opt,
+                                  int* scores_out);
+
+/* Device-resident form: pack once (2-bit codes in HBM, the resident format), score many times.
+ * All pointers are DEVICE pointers; max_short / max_long bound min(len1,len2) / max(len1,len2) over the
+ * batch; total_cells (sum of len1*len2) is only recorded for swb200_last_run.  d_scores: npairs ints. */
+typedef struct swb200_batch swb200_batch;
+SWB200_API int swb200_batch_pack_device(swb200_ctx* ctx, const unsigned char* d_seq1_all, const long long* d_off1,
+                                        const int* d_len1, const unsigned char* d_seq2_all, const long long* d_off2,
+                                        const int* d_len2, long long npairs, int max_short, int max_long,
+                                        long long total_cells, void* stream, swb200_batch** batch_out);
+SWB200_API int swb200_batch_score(swb200_batch* batch, const swb200_params* p, const swb200_options* opt,
+                                  void* stream, int* d_scores);
+SWB200_API void swb200_batch_free(swb200_batch* batch);
+
 /* ---- one very long pair over a ring of GPUs ------------------------------------------------------
  * All warps of all GPUs form one ring of DP bands: the last warp of GPU g pushes its
  * boundary stream straight into GPU g+1's memory (peer stores over NVLink), so neighbouring GPUs

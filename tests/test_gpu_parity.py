@@ -175,3 +175,45 @@ def test_ring_of_virtual_ranks_on_one_gpu(api):
         assert sum(1 for s, _ in parts if s > 0) >= 2           # the work really was spread over the ranks
     for x in rings:
         x.close()
+
+
+def _read_pairs(seed, npairs, read_len=150, win_len=1000):
+    """cfg4-style pairs: half of the reads are mutated substrings of their window, half are random."""
+    reads, wins = [], []
+    for k in range(npairs):
+        w = rng.random_acgt(seed, 2 * k, win_len if k % 7 else win_len - k % 5)
+        if k % 2 == 0:
+            off = int(rng.mix64(seed, 10**6, k) % (len(w) - read_len))
+            r = rng.mutate(w[off:off + read_len], seed, 10**6 + k, 0.05, 0.01)
+        else:
+            r = rng.random_acgt(seed, 2 * k + 1, read_len - k % 3)
+        reads.append(r); wins.append(w)
+    return reads, wins
+
+
+@pytest.mark.parametrize("no_linear", [False, True])
+def test_batch_of_reads_against_oracle(api, no_linear):
+    reads, wins = _read_pairs(700, 1500)
+    want = O.gotoh_batch(reads, wins)
+    got = api.score_batch(reads, wins, no_linear=no_linear)
+    assert got.tolist() == want.tolist()
+    assert 40 < want.max() <= 150 and want.min() < 30
+    # argument order must not matter (the kernel stripes the shorter sequence)
+    assert api.score_batch(wins, reads, no_linear=no_linear).tolist() == want.tolist()
+
+
+def test_batch_other_params_and_shapes(api):
+    reads, wins = _read_pairs(710, 300, read_len=97, win_len=333)
+    for p in ((2, -3, 5, 1), (3, -2, 2, 2), (1, -1, 4, 2)):
+        assert api.score_batch(reads, wins, p).tolist() == O.gotoh_batch(reads, wins, p).tolist(), p
+    # ragged batch incl. empty and single-base sequences, and group widths 16 / 32 (longer short sequences)
+    s1 = [b"", b"A", b"ACGT", rng.random_acgt(720, 1, 300), rng.random_acgt(720, 2, 500), rng.random_acgt(720, 3, 1000)]
+    s2 = [b"ACGT", b"A", b"", rng.mutate(s1[3], 720, 9, 0.1, 0.05), rng.random_acgt(720, 5, 700), rng.mutate(s1[5], 720, 8, 0.05, 0.02)]
+    for k in range(len(s1)):
+        assert api.score_batch(s1[k:k + 1], s2[k:k + 1]).tolist() == [O.gotoh_rolling(s1[k], s2[k])], k
+    assert api.score_batch(s1, s2).tolist() == O.gotoh_batch(s1, s2).tolist()
+    assert api.score_batch([], []).tolist() == []
+    with pytest.raises(api.SwbError):
+        api.score_batch([rng.random_acgt(1, 1, 2000)], [rng.random_acgt(1, 2, 2000)])     # > 1024: not a batch pair
+    with pytest.raises(api.SwbError):
+        api.score_batch([b"ACGN"], [b"ACGT"])
