@@ -52,7 +52,12 @@ WORKLOADS = {
 }
 RING_WORKLOADS = {"ring400k", "ring1m", "cfg3"}
 # batches of independent pairs, sharded pair-wise over the GPUs (no communication): (pairs per GPU, read, window)
-BATCH_WORKLOADS = {"cfg4": (1250000, 150, 1000), "cfg4small": (100000, 150, 1000)}
+BATCH_WORKLOADS = {"cfg4": (1250000, 150, 1000), "cfg4small": (100000, 150, 1000),
+                   # banded (64 diagonals): (pairs per GPU, len1, len2)
+                   "cfg5": (125000, 10000, 10000), "cfg5small": (10000, 10000, 10000)}
+BANDED = {"cfg5", "cfg5small"}
+WORKLOADS["cfg5"] = (10000, 10000, 5, "1M pairs / 8 GPUs = 125k pairs per GPU of 10 kb long reads, band -32..31 (64 diagonals), pair-sharded")
+WORKLOADS["cfg5small"] = (10000, 10000, 5, "10k pairs per GPU of 10 kb long reads, band -32..31")
 WORKLOADS["cfg4"] = (150, 1000, 4, "10M pairs / 8 GPUs = 1.25M pairs per GPU, 150 bp reads vs 1 kb windows, pair-sharded")
 WORKLOADS["cfg4small"] = (150, 1000, 4, "100k pairs per GPU, 150 bp reads vs 1 kb windows, pair-sharded")
 
@@ -264,17 +269,36 @@ def run_batch(args, torch, dist, api, world, rank, local):
     """Many independent pairs per GPU (BASELINE config 4), no communication on the data path (weak scaling)."""
     import oracle_lib as O
     npairs, rl, wl = BATCH_WORKLOADS[args.workload]
+    banded = args.workload in BANDED
     g = torch.Generator(device="cuda"); g.manual_seed(4000 + rank)
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
-    wins = lut[torch.randint(0, 4, (npairs, wl), generator=g, device="cuda", dtype=torch.uint8).long()]
-    # reads: even pairs = a window substring with ~5% substitutions, odd pairs = random
-    offs = torch.randint(0, wl - rl, (npairs,), generator=g, device="cuda")
-    idx = offs[:, None] + torch.arange(rl, device="cuda")[None, :]
-    reads = torch.gather(wins, 1, idx)
-    noise = lut[torch.randint(0, 4, (npairs, rl), generator=g, device="cuda", dtype=torch.uint8).long()]
-    sub = torch.rand((npairs, rl), generator=g, device="cuda") < 0.05
-    odd = (torch.arange(npairs, device="cuda") % 2 == 1)[:, None]
-    reads = torch.where(sub | odd, noise, reads).contiguous()
+
+    def rand_acgt(rows, cols):
+        out = torch.empty((rows, cols), dtype=torch.uint8, device="cuda")
+        for r0 in range(0, rows, 16384):           # chunked: the int64 index tensor of lut[] is 8x the output
+            r1 = min(rows, r0 + 16384)
+            out[r0:r1] = lut[torch.randint(0, 4, (r1 - r0, cols), generator=g, device="cuda", dtype=torch.uint8).long()]
+        return out
+
+    wins = rand_acgt(npairs, wl)
+    if banded:
+        # long reads: seq1 = seq2 with ~10% substitutions (every 4th pair unrelated), so the optimum stays in the band
+        reads = wins.clone()
+        for r0 in range(0, npairs, 16384):
+            r1 = min(npairs, r0 + 16384)
+            sub = torch.rand((r1 - r0, rl), generator=g, device="cuda") < 0.10
+            unrelated = (torch.arange(r0, r1, device="cuda") % 4 == 0)[:, None]
+            noise = lut[torch.randint(0, 4, (r1 - r0, rl), generator=g, device="cuda", dtype=torch.uint8).long()]
+            reads[r0:r1] = torch.where(sub | unrelated, noise, reads[r0:r1])
+    else:
+        # reads: even pairs = a window substring with ~5% substitutions, odd pairs = random
+        offs = torch.randint(0, wl - rl, (npairs,), generator=g, device="cuda")
+        idx = offs[:, None] + torch.arange(rl, device="cuda")[None, :]
+        reads = torch.gather(wins, 1, idx)
+        noise = rand_acgt(npairs, rl)
+        sub = torch.rand((npairs, rl), generator=g, device="cuda") < 0.05
+        odd = (torch.arange(npairs, device="cuda") % 2 == 1)[:, None]
+        reads = torch.where(sub | odd, noise, reads).contiguous()
     wins = wins.contiguous()
     off1 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * rl).contiguous()
     off2 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * wl).contiguous()
@@ -283,15 +307,32 @@ def run_batch(args, torch, dist, api, world, rank, local):
     scores = torch.zeros(npairs, dtype=torch.int32, device="cuda")
     ctx = api.Context(local)
     stream = torch.cuda.current_stream()
-    cells = float(npairs) * rl * wl
+    lo, hi = -32, 31
+    if banded:     # exact in-band cell count of one n x m pair (i = row in seq2, j = column in seq1)
+        i = np.arange(1, wl + 1)
+        per_pair = int(np.maximum(0, np.minimum(rl, i + hi) - np.maximum(1, i + lo) + 1).sum())
+    else:
+        per_pair = rl * wl
+    cells = float(npairs) * per_pair
     batch = api.PackedBatch(ctx, reads.data_ptr(), off1.data_ptr(), len1.data_ptr(), wins.data_ptr(), off2.data_ptr(),
-                            len2.data_ptr(), npairs, rl, wl, int(cells), stream=stream.cuda_stream)
+                            len2.data_ptr(), npairs, rl, wl, int(cells), stream=stream.cuda_stream, keep_order=banded)
+
+    def run_kernel():
+        if banded:
+            batch.score_banded(scores.data_ptr(), lo, hi, stream=stream.cuda_stream, no_linear=args.no_linear)
+        else:
+            batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
+
     for _ in range(max(args.warmup, 3)):
-        batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
+        run_kernel()
     # parity on a seeded sample of pairs against the oracle, every run
     sample = torch.arange(0, npairs, max(1, npairs // 512), device="cuda")[:512]
     r_h, w_h, s_h = reads[sample].cpu().numpy(), wins[sample].cpu().numpy(), scores[sample].cpu().numpy()
-    want = O.gotoh_batch(list(r_h), list(w_h))
+    if banded:
+        r_h, w_h, s_h = r_h[:64], w_h[:64], s_h[:64]
+        want = O.gotoh_banded_batch(list(r_h), list(w_h), lo, hi)
+    else:
+        want = O.gotoh_batch(list(r_h), list(w_h))
     if want.tolist() != s_h.tolist():
         raise SystemExit("bench.py: batch scores differ from the oracle on the sample")
     checksum = int(scores.to(torch.int64).sum())
@@ -303,8 +344,8 @@ def run_batch(args, torch, dist, api, world, rank, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     kms = []
-    for _ in range(args.steps):      # 1.7 GB of packed input per pass: far larger than L2, no flush needed
-        batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
+    for _ in range(args.steps):      # 0.6-1.7 GB of packed input per pass: far larger than L2, no flush needed
+        run_kernel()
         kms.append(ctx.last_run()["engine_ms"])
     e1.record(stream)
     torch.cuda.synchronize()
@@ -312,13 +353,19 @@ def run_batch(args, torch, dist, api, world, rank, local):
     dev_ms = e0.elapsed_time(e1)
     assert int(scores.to(torch.int64).sum()) == checksum
     # end to end from host bytes on a slice of the batch (H2D of sequences, pack, kernel, D2H of the scores)
-    ne = min(npairs, 200000)
+    ne = min(npairs, 20000 if banded else 200000)
     r_e, w_e = reads[:ne].cpu().numpy().reshape(-1), wins[:ne].cpu().numpy().reshape(-1)
     o1, o2 = off1[:ne].cpu().numpy(), off2[:ne].cpu().numpy()
     l1, l2 = len1[:ne].cpu().numpy(), len2[:ne].cpu().numpy()
-    api.score_batch_flat(r_e, o1, l1, w_e, o2, l2)
+
+    def host_call():
+        if banded:
+            return api.score_banded_batch_flat(r_e, o1, l1, w_e, o2, l2, lo, hi)
+        return api.score_batch_flat(r_e, o1, l1, w_e, o2, l2)
+
+    host_call()
     t1 = time.perf_counter()
-    out = api.score_batch_flat(r_e, o1, l1, w_e, o2, l2)
+    out = host_call()
     e2e_s = time.perf_counter() - t1
     assert out.tolist() == scores[:ne].cpu().numpy().tolist()
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -328,14 +375,18 @@ def run_batch(args, torch, dist, api, world, rank, local):
     if rank == 0:
         info = ctx.last_run()
         value = cells * world * args.steps / (dev_ms * 1e-3) / 1e9
-        e2e_val = float(ne) * rl * wl * world / (e2e_ms * 1e-3) / 1e9
+        e2e_val = float(ne) * per_pair * world / (e2e_ms * 1e-3) / 1e9
         f_mhz = clocks["sm_mhz"] or 1965
         peak = N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * 2 / INSTR_PER_CELL_VECTOR / 1e9
         achieved = cells / (float(np.mean(kms)) * 1e-3) / 1e9
         # reference CPU on a sample: one reference call per pair, spread over the host cores
         nb = 2000
         t0 = time.perf_counter()
-        if O.ref_available():
+        if banded:
+            cores = O.oracle().oracle_max_threads()
+            O.gotoh_banded_batch(list(r_h) * 4, list(w_h) * 4, lo, hi)
+            nb, kind = 4 * len(r_h), "port"
+        elif O.ref_available():
             import ctypes as C
             f1, o1s, l1s = O._batch_args(list(r_h) * 4)
             f2, o2s, l2s = O._batch_args(list(w_h) * 4)
@@ -350,7 +401,7 @@ def run_batch(args, torch, dist, api, world, rank, local):
             cores = O.oracle().oracle_max_threads()
             O.gotoh_batch(list(r_h) * 4, list(w_h) * 4)
             nb, kind = 4 * len(r_h), "port"
-        cpu_g = nb * rl * wl / (time.perf_counter() - t0) / 1e9
+        cpu_g = nb * (rl * wl if not banded else per_pair) / (time.perf_counter() - t0) / 1e9
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
@@ -359,12 +410,14 @@ def run_batch(args, torch, dist, api, world, rank, local):
                            "sample_checked_against_oracle": int(len(s_h))},
                 "clocks": clocks, "gpu_launches": args.steps,
                 "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(ne * (rl + wl + 24)),
-                        "d2h_bytes_per_step": int(4 * ne), "call": f"swb200_score_batch(host bytes) on {ne} pairs per GPU, wall clock"},
+                        "d2h_bytes_per_step": int(4 * ne), "call": f"swb200_score{'_banded' if banded else ''}_batch(host bytes) on {ne} pairs per GPU, wall clock"},
                 "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
                              "frac": round(achieved / peak, 4), "traffic": None,
                              "note": f"batch kernel, one GPU; peak = 148 SM x {f_mhz} MHz x L=64 x V=2 / 7"},
                 "cpu_baseline": {"value": round(cpu_g, 3), "unit": "GCUPS", "cores": cores, "kind": kind,
-                                 "sample": f"{nb} pairs of the batch, one ParallelLazySmith_threads call per pair, pairs spread over {cores} host threads"}}
+                                 "sample": (f"{nb} pairs of the batch, oracle_gotoh_banded per pair over {cores} threads (the reference has no banded mode)"
+                                            if banded else
+                                            f"{nb} pairs of the batch, one ParallelLazySmith_threads call per pair, pairs spread over {cores} host threads")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

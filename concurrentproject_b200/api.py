@@ -170,16 +170,49 @@ def score_batch_flat(flat1: np.ndarray, off1: np.ndarray, len1: np.ndarray, flat
     return out
 
 
+def score_banded_batch(seqs1, seqs2, band_lo: int = -32, band_hi: int = 31, params: Sequence[int] = DEFAULT_PARAMS, *,
+                       no_linear: bool = False) -> np.ndarray:
+    """Banded scores of many HOST pairs: cell (i, j) counts iff band_lo <= j - i <= band_hi (64 diagonals)."""
+    if len(seqs1) != len(seqs2):
+        raise ValueError("seqs1 and seqs2 differ in length")
+    f1, o1, l1 = _flatten(seqs1)
+    f2, o2, l2 = _flatten(seqs2)
+    out = np.zeros(len(seqs1), dtype=np.int32)
+    p, o = _params(params), _options(no_linear=no_linear)
+    LL, I = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+    rc = _lib.load().swb200_score_banded_batch(_ptr(f1), o1.ctypes.data_as(LL), l1.ctypes.data_as(I), _ptr(f2),
+                                               o2.ctypes.data_as(LL), l2.ctypes.data_as(I), len(seqs1), band_lo, band_hi,
+                                               C.byref(p), C.byref(o), out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_banded_batch")
+    return out
+
+
+def score_banded_batch_flat(flat1, off1, len1, flat2, off2, len2, band_lo: int = -32, band_hi: int = 31,
+                            params: Sequence[int] = DEFAULT_PARAMS, *, no_linear: bool = False) -> np.ndarray:
+    """swb200_score_banded_batch on already flattened HOST arrays."""
+    n = len(len1)
+    out = np.zeros(n, dtype=np.int32)
+    p, o = _params(params), _options(no_linear=no_linear)
+    LL, I = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+    rc = _lib.load().swb200_score_banded_batch(_ptr(flat1), off1.ctypes.data_as(LL), len1.ctypes.data_as(I), _ptr(flat2),
+                                               off2.ctypes.data_as(LL), len2.ctypes.data_as(I), n, band_lo, band_hi, C.byref(p),
+                                               C.byref(o), out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_banded_batch")
+    return out
+
+
 class PackedBatch:
     """A batch packed into the HBM-resident 2-bit format (swb200_batch_*).  All arguments are device addresses."""
 
     def __init__(self, ctx: Context, d_seq1: int, d_off1: int, d_len1: int, d_seq2: int, d_off2: int, d_len2: int, npairs: int,
-                 max_short: int, max_long: int, total_cells: int, stream: int = 0):
+                 max_short: int, max_long: int, total_cells: int, stream: int = 0, keep_order: bool = False):
         self.ctx, self.npairs = ctx, npairs
         self.handle = C.c_void_p()
         rc = _lib.load().swb200_batch_pack_device(ctx.handle, C.c_void_p(d_seq1), C.c_void_p(d_off1), C.c_void_p(d_len1),
                                                   C.c_void_p(d_seq2), C.c_void_p(d_off2), C.c_void_p(d_len2), npairs, max_short,
-                                                  max_long, total_cells, C.c_void_p(stream), C.byref(self.handle))
+                                                  max_long, total_cells, int(keep_order), C.c_void_p(stream), C.byref(self.handle))
         if rc != 0:
             raise SwbError(rc, "swb200_batch_pack_device")
 
@@ -189,6 +222,14 @@ class PackedBatch:
         rc = _lib.load().swb200_batch_score(self.handle, C.byref(p), C.byref(o), C.c_void_p(stream), C.c_void_p(d_scores))
         if rc != 0:
             raise SwbError(rc, "swb200_batch_score")
+
+    def score_banded(self, d_scores: int, band_lo: int, band_hi: int, params: Sequence[int] = DEFAULT_PARAMS, *, stream: int = 0,
+                     no_linear: bool = False) -> None:
+        p, o = _params(params), _options(no_linear=no_linear)
+        rc = _lib.load().swb200_batch_score_banded(self.handle, band_lo, band_hi, C.byref(p), C.byref(o), C.c_void_p(stream),
+                                                   C.c_void_p(d_scores))
+        if rc != 0:
+            raise SwbError(rc, "swb200_batch_score_banded")
 
     def close(self):
         if self.handle:

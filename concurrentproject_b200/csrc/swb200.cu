@@ -9,6 +9,7 @@
 #include "../../include/algoGPU.h"
 #include "swb_kernels.cuh"
 #include "swb_batch.cuh"
+#include "swb_banded.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -140,8 +141,8 @@ struct swb200_ctx {
 namespace swb {
 void launch_pack_batch(const uint8_t* seq1, const long long* off1, const int* len1, const uint8_t* seq2,
                        const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
-                       uint64_t* q_words, uint64_t* t_words, int* q_len, int* t_len, int* status, int blocks,
-                       cudaStream_t s);
+                       uint64_t* q_words, uint64_t* t_words, int* q_len, int* t_len, int keep_order, int* status,
+                       int blocks, cudaStream_t s);
 }
 
 // A packed batch resident in HBM (2-bit codes, fixed word strides, shorter sequence of each pair first).
@@ -149,6 +150,7 @@ struct swb200_batch {
   swb200_ctx* ctx = nullptr;
   long long npairs = 0, q_stride = 0, t_stride = 0;
   int max_short = 0, max_long = 0;
+  int keep_order = 0;          // 1: q = seq1, t = seq2 exactly as given (banded scoring needs j-i)
   uint64_t* q_words = nullptr;
   uint64_t* t_words = nullptr;
   int* q_len = nullptr;
@@ -557,16 +559,17 @@ int swb200_last_run(swb200_ctx* c, swb200_run_info* info) {
 // ---- batches of independent pairs --------------------------------------------------------------------
 int swb200_batch_pack_device(swb200_ctx* c, const unsigned char* d_seq1, const long long* d_off1, const int* d_len1,
                              const unsigned char* d_seq2, const long long* d_off2, const int* d_len2, long long npairs,
-                             int max_short, int max_long, long long total_cells, void* stream, swb200_batch** out) {
-  if (!c || !out || npairs < 0 || max_short < 0 || max_long < max_short)
+                             int max_short, int max_long, long long total_cells, int keep_order, void* stream,
+                             swb200_batch** out) {
+  if (!c || !out || npairs < 0 || max_short < 0 || max_long < 0 || (!keep_order && max_long < max_short))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
-  if (max_short > 1024) return fail(SWB200_ERR_ARG, "batch kernel needs min(len1,len2) <= 1024 per pair; use swb200_score for long pairs");
   std::lock_guard<std::mutex> lk(c->mu);
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   swb200_batch* b = new swb200_batch();
   b->ctx = c; b->npairs = npairs; b->max_short = max_short; b->max_long = max_long; b->cells = total_cells;
-  b->q_stride = std::max(1, (max_short + 31) / 32);
+  b->keep_order = keep_order ? 1 : 0;
+  b->q_stride = std::max(1, (max_short + 31) / 32) + (keep_order ? 2 : 0);
   b->t_stride = std::max(1, (max_long + 31) / 32) + 2;      // +2: the kernel prefetches one word past the end
   const size_t np = (size_t)std::max<long long>(npairs, 1);
   SWB_CUDA(cudaMalloc(&b->q_words, np * b->q_stride * sizeof(uint64_t)));
@@ -578,7 +581,7 @@ int swb200_batch_pack_device(swb200_ctx* c, const unsigned char* d_seq1, const l
     const long long total = npairs * (b->q_stride + b->t_stride);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);
     swb::launch_pack_batch(d_seq1, d_off1, d_len1, d_seq2, d_off2, d_len2, npairs, b->q_stride, b->t_stride, b->q_words,
-                           b->t_words, b->q_len, b->t_len, c->d_result, blocks, s);
+                           b->t_words, b->q_len, b->t_len, b->keep_order, c->d_result, blocks, s);
     SWB_CUDA(cudaGetLastError());
   }
   SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -600,6 +603,9 @@ int swb200_batch_score(swb200_batch* b, const swb200_params* pp, const swb200_op
   const swb200_options o = oo ? *oo : swb200_options{};
   int rc;
   if ((rc = check_params(p))) return rc;
+  if (b->keep_order) return fail(SWB200_ERR_ARG, "batch was packed in caller order (banded); re-pack with keep_order=0");
+  if (b->max_short > 1024)
+    return fail(SWB200_ERR_ARG, "batch kernel needs min(len1,len2) <= 1024 per pair; use swb200_score for long pairs");
   if ((long long)p.match * b->max_short > 32767 - p.match - 1)
     return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the batch kernel");
   SWB_CUDA(cudaSetDevice(c->device));
@@ -639,6 +645,47 @@ int swb200_batch_score(swb200_batch* b, const swb200_params* pp, const swb200_op
   return SWB200_OK;
 }
 
+int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const swb200_params* pp, const swb200_options* oo,
+                              void* stream, int* d_scores) {
+  if (!b || !d_scores) return fail(SWB200_ERR_ARG, "bad batch arguments");
+  if (!b->keep_order) return fail(SWB200_ERR_ARG, "banded scoring needs a batch packed with keep_order=1");
+  if (band_hi - band_lo != swb::kBandWidth - 1) return fail(SWB200_ERR_ARG, "the banded kernel handles exactly 64 diagonals");
+  swb200_ctx* c = b->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  const swb200_options o = oo ? *oo : swb200_options{};
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  if ((long long)p.match * std::min(b->max_short, b->max_long) > 32767 - p.match - 1)
+    return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the banded kernel");
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  c->info = swb200_run_info{};
+  c->info.cells = b->cells;
+  if (b->npairs == 0) return SWB200_OK;
+  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
+  const void* kern = swb::banded_kernel(mode);
+  swb::BandedParams P{};
+  P.a_words = b->q_words; P.b_words = b->t_words; P.a_len = b->q_len; P.b_len = b->t_len;
+  P.a_stride = b->q_stride; P.b_stride = b->t_stride; P.npairs = b->npairs; P.band_lo = band_lo; P.scores = d_scores;
+  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
+  int per_sm = 0;
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  per_sm = std::max(per_sm, 1);
+  const long long groups = (b->npairs + 1) / 2;
+  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
+  void* args[] = {&P};
+  SWB_CUDA(cudaEventRecord(c->ev0, s));
+  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
+  SWB_CUDA(cudaEventRecord(c->ev1, s));
+  SWB_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->info.lanes = 16; c->info.linear = mode == 1; c->info.rows = 0; c->info.config = 200; c->info.ctas = (int)ctas;
+  c->info.warps = (int)ctas * 8; c->info.bands = swb::kBandWidth; c->info.engine_launches = 1; c->info.engine_ms = ms;
+  return SWB200_OK;
+}
+
 void swb200_batch_free(swb200_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
@@ -646,9 +693,10 @@ void swb200_batch_free(swb200_batch* b) {
   delete b;
 }
 
-int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
-                       const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
-                       const swb200_params* p, const swb200_options* opt, int* scores_out) {
+static int score_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                            const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                            const swb200_params* p, const swb200_options* opt, int banded, int band_lo, int band_hi,
+                            int* scores_out) {
   if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !scores_out)))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   if (npairs == 0) return SWB200_OK;
@@ -661,8 +709,11 @@ int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, con
     if (len1[k] < 0 || len2[k] < 0 || off1[k] < 0 || off2[k] < 0) return fail(SWB200_ERR_ARG, "negative length or offset");
     bytes1 = std::max(bytes1, off1[k] + len1[k]);
     bytes2 = std::max(bytes2, off2[k] + len2[k]);
-    max_short = std::max(max_short, std::min(len1[k], len2[k]));
-    max_long = std::max(max_long, std::max(len1[k], len2[k]));
+    if (banded) { max_short = std::max(max_short, len1[k]); max_long = std::max(max_long, len2[k]); }
+    else {
+      max_short = std::max(max_short, std::min(len1[k], len2[k]));
+      max_long = std::max(max_long, std::max(len1[k], len2[k]));
+    }
     cells += (long long)len1[k] * len2[k];
   }
   uint8_t *d1 = nullptr, *d2 = nullptr;
@@ -685,8 +736,8 @@ int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, con
     SWB_CUDA(cudaMemcpyAsync(dl1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
     SWB_CUDA(cudaMemcpyAsync(dl2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
   }
-  rc = swb200_batch_pack_device(c, d1, do1, dl1, d2, do2, dl2, npairs, max_short, max_long, cells, s, &b);
-  if (rc == SWB200_OK) rc = swb200_batch_score(b, p, opt, s, dsc);
+  rc = swb200_batch_pack_device(c, d1, do1, dl1, d2, do2, dl2, npairs, max_short, max_long, cells, banded, s, &b);
+  if (rc == SWB200_OK) rc = banded ? swb200_batch_score_banded(b, band_lo, band_hi, p, opt, s, dsc) : swb200_batch_score(b, p, opt, s, dsc);
   if (rc == SWB200_OK) {
     cudaError_t e = cudaMemcpyAsync(scores_out, dsc, npairs * sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -695,6 +746,20 @@ int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, con
   swb200_batch_free(b);
   cudaFree(d1); cudaFree(d2); cudaFree(do1); cudaFree(do2); cudaFree(dl1); cudaFree(dl2); cudaFree(dsc);
   return rc;
+}
+
+int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                       const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                       const swb200_params* p, const swb200_options* opt, int* scores_out) {
+  return score_batch_host(seq1_all, off1, len1, seq2_all, off2, len2, npairs, p, opt, 0, 0, 0, scores_out);
+}
+
+int swb200_score_banded_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                              const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                              int band_lo, int band_hi, const swb200_params* p, const swb200_options* opt,
+                              int* scores_out) {
+  if (band_hi - band_lo != swb::kBandWidth - 1) return fail(SWB200_ERR_ARG, "the banded kernel handles exactly 64 diagonals");
+  return score_batch_host(seq1_all, off1, len1, seq2_all, off2, len2, npairs, p, opt, 1, band_lo, band_hi, scores_out);
 }
 
 // ---- one pair over a ring of GPUs (one swb200_ring per GPU / per process) -------------------------

@@ -1,5 +1,6 @@
 // swb_batch.cu -- instantiates the batch kernels (swb_batch.cuh) and the batch packer.
 #include "swb_batch.cuh"
+#include "swb_banded.cuh"
 
 namespace swb {
 
@@ -22,6 +23,10 @@ const void* batch_kernel(int R, int mode, int G) {
   return G == 8 ? batch_lookup<1, 8>(R) : (G == 16 ? batch_lookup<1, 16>(R) : batch_lookup<1, 32>(R));
 }
 
+const void* banded_kernel(int mode) {
+  return mode == 0 ? (const void*)sw_banded_kernel<0> : (const void*)sw_banded_kernel<1>;
+}
+
 // Packs a batch: for every pair the shorter sequence becomes Q, the longer one T; both as 2-bit codes,
 // 32 per 64-bit word, fixed word strides per pair.  One thread per output word.
 __global__ void pack_batch_kernel(const uint8_t* __restrict__ seq1, const long long* __restrict__ off1,
@@ -29,7 +34,7 @@ __global__ void pack_batch_kernel(const uint8_t* __restrict__ seq1, const long l
                                   const long long* __restrict__ off2, const int* __restrict__ len2, long long npairs,
                                   long long q_stride, long long t_stride, uint64_t* __restrict__ q_words,
                                   uint64_t* __restrict__ t_words, int* __restrict__ q_len, int* __restrict__ t_len,
-                                  int* status) {
+                                  int keep_order, int* status) {
   const long long per_pair = q_stride + t_stride;
   const long long total = npairs * per_pair;
   int bad = 0;
@@ -38,7 +43,7 @@ __global__ void pack_batch_kernel(const uint8_t* __restrict__ seq1, const long l
     const long long pair = idx / per_pair;
     const long long wi = idx - pair * per_pair;
     const int l1 = len1[pair], l2 = len2[pair];
-    const bool swap = l1 > l2;                       // Q = the shorter one
+    const bool swap = !keep_order && l1 > l2;        // Q = the shorter one, unless the caller's order matters (banded)
     const uint8_t* q = swap ? seq2 + off2[pair] : seq1 + off1[pair];
     const uint8_t* t = swap ? seq1 + off1[pair] : seq2 + off2[pair];
     const int lq = swap ? l2 : l1, lt = swap ? l1 : l2;
@@ -62,10 +67,10 @@ __global__ void pack_batch_kernel(const uint8_t* __restrict__ seq1, const long l
 
 void launch_pack_batch(const uint8_t* seq1, const long long* off1, const int* len1, const uint8_t* seq2,
                        const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
-                       uint64_t* q_words, uint64_t* t_words, int* q_len, int* t_len, int* status, int blocks,
-                       cudaStream_t s) {
+                       uint64_t* q_words, uint64_t* t_words, int* q_len, int* t_len, int keep_order, int* status,
+                       int blocks, cudaStream_t s) {
   pack_batch_kernel<<<blocks, 256, 0, s>>>(seq1, off1, len1, seq2, off2, len2, npairs, q_stride, t_stride, q_words, t_words,
-                                           q_len, t_len, status);
+                                           q_len, t_len, keep_order, status);
 }
 
 }  // namespace swb

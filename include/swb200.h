@@ -106,15 +106,30 @@ SWB200_API int swb200_score_batch(const unsigned char* seq1_all, const long long
 
 /* Device-resident form: pack once (2-bit codes in HBM, the resident format), score many times.
  * All pointers are DEVICE pointers; max_short / max_long bound min(len1,len2) / max(len1,len2) over the
- * batch; total_cells (sum of len1*len2) is only recorded for swb200_last_run.  d_scores: npairs ints. */
+ * batch; total_cells (sum of len1*len2) is only recorded for swb200_last_run.  d_scores: npairs ints.
+ * keep_order = 0: the shorter sequence of each pair is striped across lanes (full DP, swb200_batch_score);
+ * keep_order = 1: seq1 stays the column sequence, seq2 the row sequence (needed by the banded kernel, where
+ * j - i matters); max_short / max_long then bound len1 / len2. */
 typedef struct swb200_batch swb200_batch;
 SWB200_API int swb200_batch_pack_device(swb200_ctx* ctx, const unsigned char* d_seq1_all, const long long* d_off1,
                                         const int* d_len1, const unsigned char* d_seq2_all, const long long* d_off2,
                                         const int* d_len2, long long npairs, int max_short, int max_long,
-                                        long long total_cells, void* stream, swb200_batch** batch_out);
+                                        long long total_cells, int keep_order, void* stream,
+                                        swb200_batch** batch_out);
 SWB200_API int swb200_batch_score(swb200_batch* batch, const swb200_params* p, const swb200_options* opt,
                                   void* stream, int* d_scores);
 SWB200_API void swb200_batch_free(swb200_batch* batch);
+
+/* ---- banded batches (long reads): cell (i,j), i = row in seq2, j = column in seq1, is scored iff
+ * band_lo <= j - i <= band_hi; everything outside the band is H=E=F=0 and excluded from the max.  The reference
+ * has no banded mode; semantics = main.cpp:57-63 restricted to the band (oracle: oracle_gotoh_banded).
+ * This kernel handles exactly 64 diagonals: band_hi == band_lo + 63. */
+SWB200_API int swb200_score_banded_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                                         const unsigned char* seq2_all, const long long* off2, const int* len2,
+                                         long long npairs, int band_lo, int band_hi, const swb200_params* p,
+                                         const swb200_options* opt, int* scores_out);
+SWB200_API int swb200_batch_score_banded(swb200_batch* batch, int band_lo, int band_hi, const swb200_params* p,
+                                         const swb200_options* opt, void* stream, int* d_scores);
 
 /* ---- one very long pair over a ring of GPUs ------------------------------------------------------
  * All warps of all GPUs form one ring of DP bands: the last warp of GPU g pushes its

@@ -217,3 +217,37 @@ def test_batch_other_params_and_shapes(api):
         api.score_batch([rng.random_acgt(1, 1, 2000)], [rng.random_acgt(1, 2, 2000)])     # > 1024: not a batch pair
     with pytest.raises(api.SwbError):
         api.score_batch([b"ACGN"], [b"ACGT"])
+
+
+def _long_read_pairs(seed, npairs, n):
+    """cfg5-style pairs: seq2 = seq1 with 10% substitutions and 2% short indels, so the optimum stays near the diagonal."""
+    s1, s2 = [], []
+    for k in range(npairs):
+        a = rng.random_acgt(seed, k, n - (k % 3) * 7)
+        s1.append(a)
+        s2.append(rng.mutate(a, seed, 5000 + k, 0.10, 0.02) if k % 4 else rng.random_acgt(seed, 9000 + k, n))
+    return s1, s2
+
+
+@pytest.mark.parametrize("no_linear", [False, True])
+def test_banded_batch_against_oracle(api, no_linear):
+    s1, s2 = _long_read_pairs(800, 24, 3000)
+    want = O.gotoh_banded_batch(s1, s2, -32, 31)
+    got = api.score_banded_batch(s1, s2, -32, 31, no_linear=no_linear)
+    assert got.tolist() == want.tolist()
+    assert want.max() > 500           # the planted similarity really is found inside the band
+    full = O.gotoh_batch(s1, s2)
+    assert (want <= full).all()       # a band can only lose alignments
+
+
+def test_banded_other_bands_params_and_edges(api):
+    s1, s2 = _long_read_pairs(810, 9, 700)
+    for lo in (-32, -31, -63, 0, -10, 5):
+        for p in (O.DEFAULT, (2, -3, 5, 1), (3, -2, 2, 2)):
+            want = O.gotoh_banded_batch(s1, s2, lo, lo + 63, p)
+            assert api.score_banded_batch(s1, s2, lo, lo + 63, p).tolist() == want.tolist(), (lo, p)
+    e1 = [b"", b"A", b"ACGT" * 5, rng.random_acgt(820, 1, 40), rng.random_acgt(820, 2, 500), rng.random_acgt(820, 3, 33)]
+    e2 = [b"ACGT", b"A", b"", rng.random_acgt(820, 4, 90), rng.random_acgt(820, 5, 100), e1[5].copy()]
+    assert api.score_banded_batch(e1, e2).tolist() == O.gotoh_banded_batch(e1, e2, -32, 31).tolist()
+    with pytest.raises(api.SwbError):
+        api.score_banded_batch(e1, e2, -10, 10)      # only 64-diagonal bands in this kernel
