@@ -439,7 +439,7 @@ def run_ring(args, torch, dist, api, world, rank, local):
     b_d = torch.from_numpy(b_h.copy()).cuda()
     al = DistributedRingAligner(local, min(n, m))
     stream = torch.cuda.current_stream()
-    lanes = 32 if min(n, m) > 250000 else 0       # random DNA scores ~0.114*N: skip the 16-bit attempt when it cannot fit
+    lanes = 32 if args.lanes32 else 0             # default: library policy (re-based 16-bit lanes for long pairs)
     scores = []
     for _ in range(max(args.warmup, 1)):
         scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
@@ -469,7 +469,8 @@ def run_ring(args, torch, dist, api, world, rank, local):
         peak = world * N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 1), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "s16x2" if info["lanes"] == 16 else "s32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": ("s16x2 re-based" if info.get("rebased") else "s16x2") if info["lanes"] == 16 else "s32", "data": "synthetic",
                 "config": {"workload": args.workload, "description": desc, "l2": "working set is registers; boundary rings stream through L2",
                            "kernel": info, "score": scores[-1]},
                 "clocks": clocks, "gpu_launches": 3 * args.steps,
@@ -490,6 +491,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes32", action="store_true", help="ring workloads: force the 32-bit kernel")
     ap.add_argument("--no-linear", action="store_true",
                     help="keep the general affine kernel although GAP_INIT == GAP_EXT (default: use the exact E/F-free kernel)")
     args = ap.parse_args()

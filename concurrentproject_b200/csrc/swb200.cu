@@ -190,8 +190,16 @@ int check_params(const swb200_params& p) {
   return SWB200_OK;
 }
 
+// Re-based 16-bit lanes are exact as long as the values one warp holds at one time, plus what they can drift
+// between two re-base decisions, stay far inside 16 bits: neighbouring cells differ by at most match + gap per
+// step, a warp spans 64*R rows and ~100 columns, decisions come every 256 steps, the trigger is +-8000.
+bool rebase_is_safe(const swb200_params& p, int R) {
+  const long long step = (long long)p.match + std::max(p.gap_init, p.gap_ext);
+  return step * (64LL * R + 96 + swb::kRebaseBlock + 64) <= 10000;
+}
+
 struct Plan {
-  int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine
+  int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine, 3/4 = 0/1 with re-based lanes
   int R, config, ctas;
   bool swap;     // Q = seq2 instead of seq1
 };
@@ -208,10 +216,10 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
   const int skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : 12.5);
+  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : (mode == 2 ? 12.5 : (mode == 3 ? 15.0 : 11.0)));
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
-  if (config == 3) cyc_step += std::max(0.0, 30.0 - (mode == 1 ? 4.0 : 6.0) * R);   // exposed SHFL latency
+  if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
   const double lag = skew + 64 + 60;
   const long long b = NB - 1, w = b % W, r = b / W;
   const double start = std::max((double)w * lag + (double)r * (double)(LT + skew), (double)b * lag);
@@ -222,7 +230,9 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   Plan pl{};
   pl.swap = o.orient ? o.orient == 2 : m > n;   // default: stripe the longer sequence across lanes
   const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
+  // lanes: 16 = packed s16, 17 = packed s16 re-based, 32 = s32
   pl.mode = lanes == 32 ? 2 : ((p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0);
+  if (lanes == 17) pl.mode += 3;
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
@@ -242,7 +252,9 @@ const void* kernel_for(const Plan& pl) {
   switch (pl.mode) {
     case 0: return swb::engine_kernel_mode0(pl.R, pl.config);
     case 1: return swb::engine_kernel_mode1(pl.R, pl.config);
-    default: return swb::engine_kernel_mode2(pl.R, pl.config);
+    case 2: return swb::engine_kernel_mode2(pl.R, pl.config);
+    case 3: return swb::engine_kernel_mode3(pl.R, pl.config);
+    default: return swb::engine_kernel_mode4(pl.R, pl.config);
   }
 }
 
@@ -271,6 +283,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int wpc = swb::config_wpc(pl.config), slack = swb::config_slack(pl.config);
   const int rpb = swb::rows_per_band(pl.R, pl.mode);
   const long long NB = (LQ + rpb - 1) / rpb;
+  if (pl.mode >= 3 && !rebase_is_safe(p, pl.R))
+    return fail(SWB200_ERR_ARG, "re-based lanes are not safe for these scoring parameters / row count");
   if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
   if (ring && NB > 1 && ring->call_epoch == 0) return fail(SWB200_ERR_ARG, "ring epoch exhausted; create a new ring");
 
@@ -284,8 +298,9 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int warps = (int)ctas * wpc;
 
   const int skew = pl.mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const long long nsteps = ((LT + skew + swb::kChunk - 1) / swb::kChunk) * swb::kChunk;
-  const int ext_shift = log2_ceil(nsteps + swb::kChunk);
+  const int align = pl.mode >= 3 ? swb::kRebaseBlock : swb::kChunk;
+  const long long nsteps = ((LT + skew + align - 1) / align) * align;
+  const int ext_shift = std::max(4, log2_ceil(nsteps + swb::kChunk));
   const long long ext_len = 1LL << ext_shift;
   // inner rings: at most 256 laps (8-bit lap tag), at least 4096 entries
   int link_shift = std::max(12, log2_ceil((nsteps + 255) / 256));
@@ -363,7 +378,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u]\n",
             c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
             c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch);
-  c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.linear = pl.mode == 1; c->info.rows = pl.R; c->info.config = pl.config;
+  c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.rebased = pl.mode >= 3; c->info.linear = pl.mode == 1 || pl.mode == 4;
+  c->info.rows = pl.R; c->info.config = pl.config;
   c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
   c->info.engine_ms = ms;
   return SWB200_OK;
@@ -384,7 +400,13 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
   SWB_CUDA(cudaSetDevice(c->device));
 
   const uint8_t* lut = nullptr;
+  // Lane width policy.  A score is at most match*min(n,m).  If that fits, plain 16-bit lanes.  Otherwise random
+  // DNA still scores only ~0.11*N, so up to ~3x the range we try plain 16-bit first (the kernel reports leaving
+  // the range) and beyond that go straight to re-based 16-bit lanes; 32-bit lanes are the last resort.
+  const long long bound = (long long)p.match * std::min(n, m);
+  const bool rb_ok = o.rebase >= 0 && o.lanes != 32 && rebase_is_safe(p, o.rows ? o.rows : 16);
   int lanes = o.lanes == 32 ? 32 : 16;
+  if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 3LL * 32767)) lanes = 17;
   // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
   // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
   // leaving the range and we repeat in 32 bits (bit-exact either way).
@@ -416,9 +438,14 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
       lut = c->d_lut;
       continue;
     }
+    if (status & swb::STATUS_REBASE_RANGE) {
+      lanes = 32;                   // never observed; the 32-bit kernel has no such limit
+      continue;
+    }
     if (status & swb::STATUS_S16_OVERFLOW) {
-      if (o.lanes == 16) return fail(SWB200_ERR_RANGE, "score leaves the 16-bit lane range");
-      lanes = 32;
+      if (o.lanes == 16 && o.rebase < 0) return fail(SWB200_ERR_RANGE, "score leaves the 16-bit lane range");
+      lanes = rb_ok ? 17 : 32;
+      if (o.lanes == 16 && !rb_ok) return fail(SWB200_ERR_RANGE, "score leaves the 16-bit lane range");
       continue;
     }
     *score_out = score;
@@ -829,7 +856,8 @@ int swb200_ring_score_device(swb200_ring* r, const unsigned char* d_seq1, long l
   c->info.cells = n * m;
   r->calls += 1;
   RingCfg cfg{r->rank, r->world, r->inbound, r->next, r->entries, r->calls < 16384 ? r->calls : 0u};
-  return run_once(c, d_seq1, n, d_seq2, m, p, o, o.lanes, nullptr, (cudaStream_t)stream, partial_score_out, status_out, &cfg);
+  const int lanes = (o.lanes == 16 && o.rebase > 0) ? 17 : o.lanes;
+  return run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, nullptr, (cudaStream_t)stream, partial_score_out, status_out, &cfg);
 }
 
 void swb200_ring_destroy(swb200_ring* r) {

@@ -44,6 +44,15 @@ SWB_HD uint32_t max16x2(uint32_t a, uint32_t b) {
   return ((uint32_t)(al > bl ? al : bl) & 0xFFFFu) | ((uint32_t)(ah > bh ? ah : bh) << 16);
 #endif
 }
+SWB_HD uint32_t min16x2(uint32_t a, uint32_t b) {
+#if SWB_DEVICE_CODE
+  return __vmins2(a, b);
+#else
+  const int al = (short)(a & 0xFFFFu), ah = (short)(a >> 16), bl = (short)(b & 0xFFFFu), bh = (short)(b >> 16);
+  return ((uint32_t)(al < bl ? al : bl) & 0xFFFFu) | ((uint32_t)(ah < bh ? ah : bh) << 16);
+#endif
+}
+SWB_HD uint32_t max3_16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 SWB_HD int addmax32(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
 SWB_HD int max3relu32(int a, int b, int c) { return __vimax3_s32_relu(a, b, c); }
 

@@ -30,7 +30,10 @@ constexpr int kChunk = 32;     // steps between boundary polls / table refills
 constexpr int kTabRing = 256;  // per-warp ring of substitution tables (one per T position), kept twice
 constexpr int kInbox = 64;     // per-warp ring of validated top-boundary values
 
-enum : int { STATUS_S16_OVERFLOW = 1, STATUS_SPIN_TIMEOUT = 2, STATUS_BAD_SYMBOL = 4 };
+enum : int { STATUS_S16_OVERFLOW = 1, STATUS_SPIN_TIMEOUT = 2, STATUS_BAD_SYMBOL = 4, STATUS_REBASE_RANGE = 8 };
+
+constexpr int kRebaseBlock = 256;     // steps between re-base decisions (re-based 16-bit mode)
+constexpr int kRebaseTrigger = 8000;  // re-centre when a live H-open leaves [-8000, 8000] relative to the base
 
 struct EngineParams {
   const uint8_t* q_codes;       // LQ codes in {0,1,2,3}; >= 4 never matches
@@ -142,8 +145,17 @@ SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned lo
 //  Packed 16-bit engine.  MODE 0: affine gaps.  MODE 1: gap_init == gap_ext (E/F eliminated).
 //  SLACK 1: a shuffled boundary value is consumed one step after it was sent (hides SHFL latency
 //  when a scheduler has a single warp); SLACK 0: consumed in the same step (shorter pipeline).
+//  RB (re-based lanes): every register holds value - base, base a warp-uniform int32 that follows the
+//  score level, so pairs whose score leaves the s16 range keep two cells per instruction.  Exact:
+//  the values a warp holds at one time differ by a bounded amount (|dH| <= max(match, gap) per cell),
+//  so they always fit 16 bits around a common base; the zero floor becomes max(.., -base); every 256
+//  steps the warp re-centres (adds a constant to all its registers) and publishes its base next to
+//  the boundary entries so the band below can translate what it receives.
 // =================================================================================================
-template <int R, int MODE, int SLACK>
+SWB_HD int hi_half_max(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a > b ? a : b; }
+SWB_HD int lo_half_min(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a < b ? a : b; }
+
+template <int R, int MODE, int SLACK, bool RB = false>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 2 + SLACK;        // T positions between neighbouring lanes
   constexpr int SKEW = 31 * SK + 1;    // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
@@ -155,8 +167,11 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   const uint32_t padw = padb * 0x01010101u;
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
   const long long LT = P.LT;
-  const long long nsteps = ((LT + SKEW + kChunk - 1) / kChunk) * kChunk;
+  constexpr int STEP_ALIGN = RB ? kRebaseBlock : kChunk;   // RB: base blocks of consecutive bands must not share a slot
+  const long long nsteps = ((LT + SKEW + STEP_ALIGN - 1) / STEP_ALIGN) * STEP_ALIGN;
   uint32_t best0 = 0, best1 = 0;
+  int base = 0, best_abs = 0;          // RB only
+  uint32_t floorw = 0;                 // RB only: packed max(-base, -30000)
   Waiter wt{P.spin_limit, false};
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
@@ -197,6 +212,13 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
     uint32_t Fbot = nopen, up_prev = nopen, xsend = nopen, yold = nopen, Thi = padw;
+    if (RB) { base = 0; floorw = 0; best0 = 0; best1 = 0; }   // every band starts at T position 0, where all scores are small
+    // base entries live in the second half of a link ring: one {base, tag} per kRebaseBlock producer steps
+    // (on the full-length ext stream, which restarts every band, four bands' worth of base entries rotate, so a
+    //  band's bases are not overwritten while the previous band's are still being read)
+    const uint2* in_bases = in + ((size_t)in_mask + 1) + (first_local ? (size_t)((band - 1) & 3) << (in_shift - 2) : 0);
+    uint2* out_bases = out + ((size_t)out_mask + 1) + (last_local ? (size_t)(band & 3) << (out_shift - 2) : 0);
+    const unsigned inb_mask = first_local ? (in_mask >> 2) : in_mask, outb_mask = last_local ? (out_mask >> 2) : out_mask;
 
     // ---- table ring: everything pad, then T positions [0, 32)
     w.sync();
@@ -212,10 +234,14 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
     }
     // ---- loads issued one chunk ahead of their use: the packed T word of positions [32,64) and a
-    //      speculative read of this lane's first boundary entry
+    //      speculative read of this lane's first boundary entry (and, re-based mode, of its producer's base)
     uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(P.t_packed + ((kChunk + lane) >> 5)) : 0ull;
-    uint2 epref = make_uint2(0u, 0u);
-    if (!zero_src && SLACK + lane < LT) epref = ld_entry(in + ((in_base + SLACK + lane + SKEW) & in_mask));
+    uint2 epref = make_uint2(0u, 0u), bpref = make_uint2(0u, 0u);
+    if (!zero_src && SLACK + lane < LT) {
+      const long long j = in_base + SLACK + lane + SKEW;
+      epref = ld_entry(in + (j & in_mask));
+      if (RB) bpref = ld_entry(in_bases + ((j >> 8) & inb_mask));
+    }
 
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
 #if SWB_DEVICE_CODE
@@ -232,10 +258,37 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
         twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
       }
+      // (a') re-based mode: every kRebaseBlock steps re-centre the registers around the live score level
+      if (RB && (i0 & (kRebaseBlock - 1)) == 0) {
+        if (i0 > 0) {
+          uint32_t mxw = Ho[0], mnw = Ho[0];
+#pragma unroll
+          for (int r = 1; r < R; ++r) { mxw = max16x2(mxw, Ho[r]); mnw = min16x2(mnw, Ho[r]); }
+          const int mx = w.reduce_max(hi_half_max(mxw));
+          const int mn = -w.reduce_max(-lo_half_min(mnw));
+          if (mx - mn > 20000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);   // never seen; host repeats in 32 bit
+          int delta = (mx > kRebaseTrigger || mn < -kRebaseTrigger) ? (mx + mn) / 2 : 0;
+          if (base + delta < 0) delta = -base;
+          if (delta != 0) {                                               // warp-uniform
+            const int b = hi_half_max(max16x2(best0, best1)) + base;
+            best_abs = best_abs > b ? best_abs : b;
+            best0 = best1 = pack2(-32768);
+            const uint32_t dw = pack2(-delta);
+#pragma unroll
+            for (int r = 0; r < R; ++r) { Ho[r] = add16x2(Ho[r], dw); E[r] = add16x2(E[r], dw); }
+            Fbot = add16x2(Fbot, dw); up_prev = add16x2(up_prev, dw); xsend = add16x2(xsend, dw); yold = add16x2(yold, dw);
+            base += delta;
+            floorw = pack2(-base > -30000 ? -base : -30000);
+          }
+        }
+        // tell the band below which base the entries of this block are relative to
+        if (emit) st_entry(out_bases + (((out_base + i0) >> 8) & outb_mask), (uint32_t)base,
+                           out_tag | ((uint32_t)(((out_base + i0) >> 8) >> out_shift) & 0xFFu));
+      }
       // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): wait for the producer
       {
         const long long q = i0 + SLACK + lane;
-        uint32_t v = nopen;
+        uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
         if (!zero_src) {                                                  // warp-uniform branch
           const bool need = q < LT;
           const long long j = in_base + q + SKEW;                         // producer step that emitted q
@@ -243,6 +296,18 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
               wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
           if (need) v = got;
           if (q + kChunk < LT) epref = ld_entry(in + ((j + kChunk) & in_mask));   // next chunk, speculative
+          if (RB) {
+            // translate from the producer's base (published once per block) into ours
+            const long long bj = j >> 8;
+            const uint32_t pb = wait_entry(P, w, need, in_bases + (bj & inb_mask),
+                                           in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
+            if (need) {
+              const int diff = (int)pb - base;
+              if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
+              v = add16x2(v, pack2(diff));
+            }
+            if (q + kChunk < LT) bpref = ld_entry(in_bases + (((j + kChunk) >> 8) & inb_mask));
+          }
         }
         sm->inbox[q & (kInbox - 1)] = v;
         sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
@@ -294,9 +359,9 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
           if (MODE == 0) {
             E[r] = addmax16x2(E[r], next, old);
             F = addmax16x2(F, next, Hup);
-            h = max3relu16x2(d, E[r], F);
+            h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
           } else {
-            h = max3relu16x2(d, old, Hup);
+            h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max3relu16x2(d, old, Hup);
           }
           Ho[r] = add16x2(h, nopen);
           Hup = Ho[r];
@@ -318,16 +383,18 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       }
 #endif
     }
+    if (RB) {
+      const int b = hi_half_max(max16x2(best0, best1)) + base;
+      best_abs = best_abs > b ? best_abs : b;
+    }
     if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + nsteps));
   }
 
   // ---- running best: halves -> int, warp max, one atomic
-  const uint32_t b = max16x2(best0, best1);
-  int bi = (int)(short)(b & 0xFFFFu), bj = (int)(short)(b >> 16);
-  int m = w.reduce_max(bi > bj ? bi : bj);
+  const int m = w.reduce_max(RB ? best_abs : hi_half_max(max16x2(best0, best1)));
   if (lane == 0) {
     atomic_max_i32(P.result, m);
-    if (m > 32767 - P.match - 1) atomic_or_i32(P.result + 1, STATUS_S16_OVERFLOW);
+    if (!RB && m > 32767 - P.match - 1) atomic_or_i32(P.result + 1, STATUS_S16_OVERFLOW);
   }
 }
 

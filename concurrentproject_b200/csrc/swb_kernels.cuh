@@ -15,10 +15,13 @@ SWB_HD int config_slack(int config) { return config == 1 ? 1 : 0; }
 constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 12, 16};
 constexpr int kNumRowChoices = 8;
 
-// mode 0: s16x2 affine, 1: s16x2 linear (gap_init == gap_ext), 2: s32 affine
+// mode 0: s16x2 affine, 1: s16x2 linear (gap_init == gap_ext), 2: s32 affine,
+// mode 3 / 4: modes 0 / 1 with re-based lanes (scores beyond the s16 range at the packed rate)
 const void* engine_kernel_mode0(int R, int config);
 const void* engine_kernel_mode1(int R, int config);
 const void* engine_kernel_mode2(int R, int config);
+const void* engine_kernel_mode3(int R, int config);
+const void* engine_kernel_mode4(int R, int config);
 
 #ifdef __CUDACC__
 template <int R, int MODE, int SLACK, int WPC>
@@ -28,6 +31,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   const int wi = (int)(threadIdx.x >> 5);
   const int lw = (int)blockIdx.x * WPC + wi;
   if constexpr (MODE == 2) engine_warp_s32<R, SLACK>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true>(P, w, lw, &sm[wi]);
   else engine_warp_s16<R, MODE, SLACK>(P, w, lw, &sm[wi]);
 }
 

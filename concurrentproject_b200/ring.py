@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 from . import _lib
 from .api import DEFAULT_PARAMS, Context, SwbError, _options, _params
 
-STATUS_S16_OVERFLOW, STATUS_TIMEOUT = 1, 2
+STATUS_S16_OVERFLOW, STATUS_TIMEOUT, STATUS_REBASE_RANGE = 1, 2, 8
 
 
 class Ring:
@@ -39,10 +39,10 @@ class Ring:
             raise SwbError(rc, "swb200_ring_connect_local")
 
     def partial(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int,
-                stream: int = 0, rows: int = 0, config: int = 0, ctas: int = 0, no_linear: bool = False):
+                stream: int = 0, rows: int = 0, config: int = 0, ctas: int = 0, no_linear: bool = False, rebase: int = 0):
         """This rank's share of one collective call: (partial best score, status bits)."""
         score, status = C.c_int(0), C.c_int(0)
-        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear)
+        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, 0, rebase)
         rc = _lib.load().swb200_ring_score_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
                                                   C.byref(o), C.c_void_p(stream), C.byref(score), C.byref(status))
         if rc != 0:
@@ -75,20 +75,35 @@ class DistributedRingAligner:
 
     def score(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0,
               stream: int = 0, **opts) -> int:
+        """Collective.  Lane-width policy as in swb200_score: plain 16-bit lanes while match*min(n,m) is within ~3x
+        the s16 range (the kernel reports leaving it), then re-based 16-bit lanes, 32-bit lanes as the last resort.
+        Every rank takes the same decisions because they depend only on the arguments and on all-reduced flags."""
         torch, dist = self.torch, self.dist
-        for width in ((16, 32) if lanes == 0 else (lanes,)):
-            part, status = self.ring.partial(d_seq1, n, d_seq2, m, params, lanes=width, stream=stream, **opts)
-            t = torch.tensor([part, status & STATUS_S16_OVERFLOW, status & STATUS_TIMEOUT], dtype=torch.int32,
-                             device=self.reduce_device)
+        bound = int(params[0]) * min(n, m)
+        if lanes == 32:
+            attempts = [(32, -1)]
+        elif lanes == 16:
+            attempts = [(16, -1)]
+        else:
+            attempts = ([(16, -1)] if bound <= 3 * 32767 else []) + [(16, 1), (32, -1)]
+        for width, rebase in attempts:
+            try:
+                part, status = self.ring.partial(d_seq1, n, d_seq2, m, params, lanes=width, rebase=rebase, stream=stream, **opts)
+            except SwbError as e:
+                if rebase == 1 and e.code == -2:      # re-based lanes not safe for these parameters: same on every rank
+                    continue
+                raise
+            t = torch.tensor([part, status & STATUS_S16_OVERFLOW, status & STATUS_TIMEOUT, status & STATUS_REBASE_RANGE],
+                             dtype=torch.int32, device=self.reduce_device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            best, overflow, timeout = (int(x) for x in t.tolist())
+            best, overflow, timeout, rb_range = (int(x) for x in t.tolist())
             if timeout:
                 raise RuntimeError("ring hand-off timed out on some rank")
-            if not overflow:
+            if not overflow and not rb_range:
                 return best
             if lanes == 16:
                 raise RuntimeError("score leaves the 16-bit lane range")
-        raise RuntimeError("unreachable")
+        raise RuntimeError("no lane width could score this pair")
 
     def last_run(self) -> dict:
         return self.ctx.last_run()

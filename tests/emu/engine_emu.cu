@@ -34,7 +34,8 @@ template <int R, int MODE, int SLACK>
 static void run_lane(const EngineParams* P, WarpShared* ws, int lane, int lw, WarpSmem* sm) {
   WarpCtx w{lane, ws};
   if (MODE == 2) engine_warp_s32<R, SLACK>(*P, w, lw, sm);
-  else engine_warp_s16<R, (MODE == 2 ? 0 : MODE), SLACK>(*P, w, lw, sm);
+  else if (MODE >= 3) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true>(*P, w, lw, sm);
+  else engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK>(*P, w, lw, sm);
 }
 
 typedef void (*lane_fn)(const EngineParams*, WarpShared*, int, int, WarpSmem*);
@@ -43,6 +44,8 @@ template <int R>
 static lane_fn pick2(int mode, int slack) {
   if (mode == 0) return slack ? run_lane<R, 0, 1> : run_lane<R, 0, 0>;
   if (mode == 1) return slack ? run_lane<R, 1, 1> : run_lane<R, 1, 0>;
+  if (mode == 3) return slack ? run_lane<R, 3, 1> : run_lane<R, 3, 0>;
+  if (mode == 4) return slack ? run_lane<R, 4, 1> : run_lane<R, 4, 0>;
   return slack ? run_lane<R, 2, 1> : run_lane<R, 2, 0>;
 }
 static lane_fn pick(int R, int mode, int slack) {
@@ -77,7 +80,8 @@ int main(int argc, char** argv) {
   const int rpb = rows_per_band(R, mode);
   const int NB = (int)((LQ + rpb - 1) / rpb);
   const long long skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  long long nsteps = ((LT + skew + kChunk - 1) / kChunk) * kChunk;
+  const int align = mode >= 3 ? kRebaseBlock : kChunk;
+  long long nsteps = ((LT + skew + align - 1) / align) * align;
   long long ext_len = 1; int ext_shift = 0;
   while (ext_len < nsteps + kChunk) { ext_len <<= 1; ++ext_shift; }
   int link_shift = 0; while ((1LL << link_shift) < link_len) ++link_shift;

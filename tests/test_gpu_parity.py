@@ -109,11 +109,13 @@ def test_other_alphabets_are_remapped(api):
 def test_scores_beyond_the_s16_range_rerun_in_32_bit(api):
     a = rng.random_acgt(520, 0, 40000)
     assert api.score(a, a) == 40000                      # analytic: identical sequences score MATCH*N
-    assert api.last_run()["lanes"] == 32 and api.last_run()["engine_launches"] == 2
+    info = api.last_run()                                # plain 16-bit lanes reported the overflow, re-based lanes finished the job
+    assert info["lanes"] == 16 and info["rebased"] == 1 and info["engine_launches"] == 2
+    assert api.score(a, a, rebase=-1) == 40000 and api.last_run()["lanes"] == 32
     b = a.copy(); b[20000:20010] = np.where(b[20000:20010] == ord('A'), ord('C'), ord('A'))   # 10 substituted bases
     assert api.score(a, b) == O.gotoh_mt(a, b)
     with pytest.raises(api.SwbError) as e:
-        api.score(a, a, lanes=16)
+        api.score(a, a, lanes=16, rebase=-1)
     assert e.value.code == -6
 
 
@@ -251,3 +253,30 @@ def test_banded_other_bands_params_and_edges(api):
     assert api.score_banded_batch(e1, e2).tolist() == O.gotoh_banded_batch(e1, e2, -32, 31).tolist()
     with pytest.raises(api.SwbError):
         api.score_banded_batch(e1, e2, -10, 10)      # only 64-diagonal bands in this kernel
+
+
+@pytest.mark.parametrize("config", [1, 2, 3])
+def test_rebased_16_bit_lanes(api, config):
+    """Scores far beyond 32767 in packed 16-bit lanes relative to a moving base: the level climbs (identical
+    prefix), falls back to ~0 (unrelated middle), climbs again; every re-base direction is exercised."""
+    n = 90000
+    a = rng.random_acgt(530, 0, n)
+    b = a.copy()
+    b[40000:52000] = rng.random_acgt(530, 7, 12000)          # unrelated stretch: the score level collapses here
+    b = np.concatenate([b[:70000], b[70003:]])               # and one 3-base gap later on
+    want = O.gotoh_mt(a, b)
+    assert want > 32767
+    for rows, no_linear in ((4, False), (8, True), (16, False), (2, True)):
+        assert api.score(a, b, lanes=16, rebase=1, rows=rows, config=config, no_linear=no_linear) == want, (rows, no_linear)
+        info = api.last_run()
+        assert info["rebased"] == 1 and info["engine_launches"] == 1
+    assert api.score(a, b, lanes=32) == want
+    p = (3, -2, 4, 2)                                        # other parameters, still inside the re-base safety bound for R=4
+    assert api.score(a, b, p, lanes=16, rebase=1, rows=4, config=config) == O.gotoh_mt(a, b, p)
+
+
+def test_rebased_lanes_refuse_unsafe_parameters(api):
+    a = rng.random_acgt(531, 0, 5000)
+    with pytest.raises(api.SwbError):
+        api.score(a, a, (100, -100, 20, 20), lanes=16, rebase=1, rows=8)      # steps of 120 per cell: no safe base spacing
+    assert api.score(a, a, (100, -100, 20, 20)) == 500000                     # automatic policy falls back to 32 bit

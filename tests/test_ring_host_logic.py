@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the host-side ring orchestration (concurrentproject_b200/ring.py): handle exchange,
-neighbour wiring, max/OR reduction of the ranks' partial results, the collective 16-bit -> 32-bit retry.
+neighbour wiring, max/OR reduction of the ranks' partial results, the collective retry with re-based lanes when the score leaves the s16 range.
 The CUDA ring end points are replaced by stand-ins that behave like the C ABI (no GPU here); the real kernels
 are covered by tests/test_gpu_parity.py::test_ring_of_virtual_ranks_on_one_gpu and the multi-GPU bench."""
 import os
@@ -40,10 +40,10 @@ class FakeRing:
     def connect_local(self, other):
         self.next = other.rank
 
-    def partial(self, d1, n, d2, m, params, *, lanes, stream=0, **kw):
-        FakeRing.log.append(lanes)
+    def partial(self, d1, n, d2, m, params, *, lanes, rebase=0, stream=0, **kw):
+        FakeRing.log.append((lanes, rebase))
         true_score = 40000 if n == 99 else 1234          # n == 99: a pair whose score leaves the s16 range
-        if lanes == 16 and true_score > 32000:
+        if lanes == 16 and rebase < 0 and true_score > 32000:
             return (32700, 1) if self.rank == 1 else (17, 0)     # only ONE rank notices the overflow
         return (true_score if self.rank == self.world - 1 else 5 * self.rank, 0)
 
@@ -86,6 +86,6 @@ def test_ring_orchestration_two_ranks_gloo():
         assert p.exitcode == 0
     assert [r["next"] for r in res] == [1, 0]                       # each rank mapped its successor's buffer
     assert [r["plain"] for r in res] == [1234, 1234]                # max over partial scores, same on every rank
-    assert [r["overflow"] for r in res] == [40000, 40000]           # every rank repeated in 32-bit lanes ...
-    assert [r["widths"] for r in res] == [[16, 32], [16, 32]]       # ... although only rank 1 saw the overflow
+    assert [r["overflow"] for r in res] == [40000, 40000]           # every rank repeated the call ...
+    assert [r["widths"] for r in res] == [[(16, -1), (16, 1)]] * 2       # ... (re-based lanes) although only rank 1 saw the overflow
     assert all("16-bit" in r["forced16"] for r in res)
