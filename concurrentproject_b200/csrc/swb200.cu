@@ -401,12 +401,13 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
 
   const uint8_t* lut = nullptr;
   // Lane width policy.  A score is at most match*min(n,m).  If that fits, plain 16-bit lanes.  Otherwise random
-  // DNA still scores only ~0.11*N, so up to ~3x the range we try plain 16-bit first (the kernel reports leaving
-  // the range) and beyond that go straight to re-based 16-bit lanes; 32-bit lanes are the last resort.
+  // DNA still scores only ~0.11*N, so up to 8x the range we try plain 16-bit first (the kernel reports leaving
+  // the range; the re-based kernel is ~10% slower) and beyond that go straight to re-based 16-bit lanes;
+  // 32-bit lanes are the last resort.
   const long long bound = (long long)p.match * std::min(n, m);
   const bool rb_ok = o.rebase >= 0 && o.lanes != 32 && rebase_is_safe(p, o.rows ? o.rows : 16);
   int lanes = o.lanes == 32 ? 32 : 16;
-  if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 3LL * 32767)) lanes = 17;
+  if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 8LL * 32767)) lanes = 17;
   // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
   // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
   // leaving the range and we repeat in 32 bits (bit-exact either way).

@@ -75,7 +75,7 @@ class DistributedRingAligner:
 
     def score(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0,
               stream: int = 0, **opts) -> int:
-        """Collective.  Lane-width policy as in swb200_score: plain 16-bit lanes while match*min(n,m) is within ~3x
+        """Collective.  Lane-width policy as in swb200_score: plain 16-bit lanes while match*min(n,m) is within 8x
         the s16 range (the kernel reports leaving it), then re-based 16-bit lanes, 32-bit lanes as the last resort.
         Every rank takes the same decisions because they depend only on the arguments and on all-reduced flags."""
         torch, dist = self.torch, self.dist
@@ -85,7 +85,7 @@ class DistributedRingAligner:
         elif lanes == 16:
             attempts = [(16, -1)]
         else:
-            attempts = ([(16, -1)] if bound <= 3 * 32767 else []) + [(16, 1), (32, -1)]
+            attempts = ([(16, -1)] if bound <= 8 * 32767 else []) + [(16, 1), (32, -1)]
         for width, rebase in attempts:
             try:
                 part, status = self.ring.partial(d_seq1, n, d_seq2, m, params, lanes=width, rebase=rebase, stream=stream, **opts)
