@@ -136,6 +136,18 @@ struct swb200_ctx {
   int* h_result = nullptr;        // pinned
   unsigned epoch = 0;
   swb200_run_info info{};
+  // grow-only staging of the host batch entry points (no cudaMalloc/cudaFree per call)
+  uint8_t* hb_seq1 = nullptr; size_t hb_seq1_cap = 0;
+  uint8_t* hb_seq2 = nullptr; size_t hb_seq2_cap = 0;
+  long long* hb_off1 = nullptr; size_t hb_off1_cap = 0;
+  long long* hb_off2 = nullptr; size_t hb_off2_cap = 0;
+  int* hb_len1 = nullptr; size_t hb_len1_cap = 0;
+  int* hb_len2 = nullptr; size_t hb_len2_cap = 0;
+  int* hb_scores = nullptr; size_t hb_scores_cap = 0;
+  uint64_t* hb_qw = nullptr; size_t hb_qw_cap = 0;
+  uint64_t* hb_tw = nullptr; size_t hb_tw_cap = 0;
+  int* hb_ql = nullptr; size_t hb_ql_cap = 0;
+  int* hb_tl = nullptr; size_t hb_tl_cap = 0;
 };
 
 namespace swb {
@@ -151,6 +163,7 @@ struct swb200_batch {
   long long npairs = 0, q_stride = 0, t_stride = 0;
   int max_short = 0, max_long = 0;
   int keep_order = 0;          // 1: q = seq1, t = seq2 exactly as given (banded scoring needs j-i)
+  bool pooled = false;         // storage belongs to the context's staging pool
   uint64_t* q_words = nullptr;
   uint64_t* t_words = nullptr;
   int* q_len = nullptr;
@@ -530,6 +543,8 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_links); cudaFree(c->d_ext);
   cudaFree(c->d_progress); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
+  cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);
   cudaFreeHost(c->h_result);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -585,10 +600,22 @@ int swb200_last_run(swb200_ctx* c, swb200_run_info* info) {
 }
 
 // ---- batches of independent pairs --------------------------------------------------------------------
+static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const long long* d_off1, const int* d_len1,
+                           const unsigned char* d_seq2, const long long* d_off2, const int* d_len2, long long npairs,
+                           int max_short, int max_long, long long total_cells, int keep_order, bool pooled, void* stream,
+                           swb200_batch** out);
 int swb200_batch_pack_device(swb200_ctx* c, const unsigned char* d_seq1, const long long* d_off1, const int* d_len1,
                              const unsigned char* d_seq2, const long long* d_off2, const int* d_len2, long long npairs,
                              int max_short, int max_long, long long total_cells, int keep_order, void* stream,
                              swb200_batch** out) {
+  return batch_pack_impl(c, d_seq1, d_off1, d_len1, d_seq2, d_off2, d_len2, npairs, max_short, max_long, total_cells,
+                         keep_order, false, stream, out);
+}
+
+static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const long long* d_off1, const int* d_len1,
+                           const unsigned char* d_seq2, const long long* d_off2, const int* d_len2, long long npairs,
+                           int max_short, int max_long, long long total_cells, int keep_order, bool pooled, void* stream,
+                           swb200_batch** out) {
   if (!c || !out || npairs < 0 || max_short < 0 || max_long < 0 || (!keep_order && max_long < max_short))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   std::lock_guard<std::mutex> lk(c->mu);
@@ -600,10 +627,18 @@ int swb200_batch_pack_device(swb200_ctx* c, const unsigned char* d_seq1, const l
   b->q_stride = std::max(1, (max_short + 31) / 32) + (keep_order ? 2 : 0);
   b->t_stride = std::max(1, (max_long + 31) / 32) + 2;      // +2: the kernel prefetches one word past the end
   const size_t np = (size_t)std::max<long long>(npairs, 1);
-  SWB_CUDA(cudaMalloc(&b->q_words, np * b->q_stride * sizeof(uint64_t)));
-  SWB_CUDA(cudaMalloc(&b->t_words, np * b->t_stride * sizeof(uint64_t)));
-  SWB_CUDA(cudaMalloc(&b->q_len, np * sizeof(int)));
-  SWB_CUDA(cudaMalloc(&b->t_len, np * sizeof(int)));
+  b->pooled = pooled;
+  if (pooled) {
+    int rc;
+    if ((rc = grow(c->hb_qw, c->hb_qw_cap, np * b->q_stride, false, s)) || (rc = grow(c->hb_tw, c->hb_tw_cap, np * b->t_stride, false, s)) ||
+        (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, s)) || (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, s))) { delete b; return rc; }
+    b->q_words = c->hb_qw; b->t_words = c->hb_tw; b->q_len = c->hb_ql; b->t_len = c->hb_tl;
+  } else {
+    SWB_CUDA(cudaMalloc(&b->q_words, np * b->q_stride * sizeof(uint64_t)));
+    SWB_CUDA(cudaMalloc(&b->t_words, np * b->t_stride * sizeof(uint64_t)));
+    SWB_CUDA(cudaMalloc(&b->q_len, np * sizeof(int)));
+    SWB_CUDA(cudaMalloc(&b->t_len, np * sizeof(int)));
+  }
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
   if (npairs > 0) {
     const long long total = npairs * (b->q_stride + b->t_stride);
@@ -717,7 +752,7 @@ int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const s
 void swb200_batch_free(swb200_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
-  cudaFree(b->q_words); cudaFree(b->t_words); cudaFree(b->q_len); cudaFree(b->t_len);
+  if (!b->pooled) { cudaFree(b->q_words); cudaFree(b->t_words); cudaFree(b->q_len); cudaFree(b->t_len); }
   delete b;
 }
 
@@ -753,10 +788,12 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
     std::lock_guard<std::mutex> lk(c->mu);
     SWB_CUDA(cudaSetDevice(c->device));
     s = c->own_stream;
-    SWB_CUDA(cudaMalloc(&d1, (size_t)bytes1 + 16)); SWB_CUDA(cudaMalloc(&d2, (size_t)bytes2 + 16));
-    SWB_CUDA(cudaMalloc(&do1, npairs * sizeof(long long))); SWB_CUDA(cudaMalloc(&do2, npairs * sizeof(long long)));
-    SWB_CUDA(cudaMalloc(&dl1, npairs * sizeof(int))); SWB_CUDA(cudaMalloc(&dl2, npairs * sizeof(int)));
-    SWB_CUDA(cudaMalloc(&dsc, npairs * sizeof(int)));
+    const size_t np = (size_t)npairs;
+    if ((rc = grow(c->hb_seq1, c->hb_seq1_cap, (size_t)bytes1 + 16, false, s)) || (rc = grow(c->hb_seq2, c->hb_seq2_cap, (size_t)bytes2 + 16, false, s)) ||
+        (rc = grow(c->hb_off1, c->hb_off1_cap, np, false, s)) || (rc = grow(c->hb_off2, c->hb_off2_cap, np, false, s)) ||
+        (rc = grow(c->hb_len1, c->hb_len1_cap, np, false, s)) || (rc = grow(c->hb_len2, c->hb_len2_cap, np, false, s)) ||
+        (rc = grow(c->hb_scores, c->hb_scores_cap, np, false, s))) return rc;
+    d1 = c->hb_seq1; d2 = c->hb_seq2; do1 = c->hb_off1; do2 = c->hb_off2; dl1 = c->hb_len1; dl2 = c->hb_len2; dsc = c->hb_scores;
     SWB_CUDA(cudaMemcpyAsync(d1, seq1_all, (size_t)bytes1, cudaMemcpyHostToDevice, s));
     SWB_CUDA(cudaMemcpyAsync(d2, seq2_all, (size_t)bytes2, cudaMemcpyHostToDevice, s));
     SWB_CUDA(cudaMemcpyAsync(do1, off1, npairs * sizeof(long long), cudaMemcpyHostToDevice, s));
@@ -764,7 +801,7 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
     SWB_CUDA(cudaMemcpyAsync(dl1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
     SWB_CUDA(cudaMemcpyAsync(dl2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
   }
-  rc = swb200_batch_pack_device(c, d1, do1, dl1, d2, do2, dl2, npairs, max_short, max_long, cells, banded, s, &b);
+  rc = batch_pack_impl(c, d1, do1, dl1, d2, do2, dl2, npairs, max_short, max_long, cells, banded, true, s, &b);
   if (rc == SWB200_OK) rc = banded ? swb200_batch_score_banded(b, band_lo, band_hi, p, opt, s, dsc) : swb200_batch_score(b, p, opt, s, dsc);
   if (rc == SWB200_OK) {
     cudaError_t e = cudaMemcpyAsync(scores_out, dsc, npairs * sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -772,7 +809,6 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
     if (e != cudaSuccess) rc = fail(SWB200_ERR_CUDA, std::string("batch result copy: ") + cudaGetErrorString(e));
   }
   swb200_batch_free(b);
-  cudaFree(d1); cudaFree(d2); cudaFree(do1); cudaFree(do2); cudaFree(dl1); cudaFree(dl2); cudaFree(dsc);
   return rc;
 }
 
