@@ -1,11 +1,13 @@
-import sys, time, os
-sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import sys, os; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np, oracle_lib as O
 from concurrentproject_b200 import api, rng
-LT = 60000
-t = rng.random_acgt(7,1,LT)
-for lanes,rows,config,nb in [(16,2,1,1),(16,2,1,2),(16,2,1,4),(16,8,1,2)]:
-    rpb = (64 if lanes==16 else 32)*rows
-    q = rng.random_acgt(7,0,rpb*nb)
-    s = api.score(q,t,lanes=lanes,rows=rows,config=config,no_linear=True,orient=1)
-    info = api.last_run()
-    print(f"dbg={os.environ.get('SWB200_DBG')} lanes={lanes} rows={rows} config={config} bands={info['bands']} ms={info['engine_ms']:.3f} ns/step={info['engine_ms']*1e6/LT:.1f}", flush=True)
+found=[]
+for p in ((3,-2,2,2),(1,-1,1,1),(2,-3,5,1)):
+  for n in (520, 600, 700, 1000, 1500, 2000, 3000):
+    for seed in range(12):
+        a = rng.random_acgt(2000+seed, 0, n); b = rng.random_acgt(2000+seed, 1, n)
+        want = O.gotoh_rolling(a,b,p)
+        for cfg in (1,3):
+            got = api.score(a,b,p,rows=1,config=cfg,two_sided=1)
+            if got != want: found.append((p,n,seed,cfg,got,want)); print('BAD',p,n,seed,cfg,got,want,flush=True)
+print('total bad',len(found))

@@ -19,11 +19,11 @@ class Params(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("lanes", C.c_int), ("rows", C.c_int), ("config", C.c_int), ("ctas", C.c_int),
-                ("no_linear", C.c_int), ("orient", C.c_int), ("rebase", C.c_int), ("reserved", C.c_int * 1)]
+                ("no_linear", C.c_int), ("orient", C.c_int), ("rebase", C.c_int), ("two_sided", C.c_int)]
 
 
 class RunInfo(C.Structure):
-    _fields_ = [("lanes", C.c_int), ("rebased", C.c_int), ("linear", C.c_int), ("rows", C.c_int), ("config", C.c_int),
+    _fields_ = [("lanes", C.c_int), ("rebased", C.c_int), ("two_sided", C.c_int), ("linear", C.c_int), ("rows", C.c_int), ("config", C.c_int),
                 ("ctas", C.c_int), ("warps", C.c_int), ("bands", C.c_int), ("engine_launches", C.c_int),
                 ("aux_launches", C.c_int), ("cells", C.c_longlong), ("engine_ms", C.c_float)]
 

@@ -37,10 +37,10 @@ def _params(p) -> Params:
     return Params(int(m), int(x), int(gi), int(ge))
 
 
-def _options(lanes=0, rows=0, config=0, ctas=0, no_linear=False, orient=0, rebase=0) -> Options:
+def _options(lanes=0, rows=0, config=0, ctas=0, no_linear=False, orient=0, rebase=0, two_sided=0) -> Options:
     o = Options()
     o.lanes, o.rows, o.config, o.ctas, o.no_linear, o.orient = lanes, rows, config, ctas, int(bool(no_linear)), orient
-    o.rebase = rebase
+    o.rebase, o.two_sided = rebase, two_sided
     return o
 
 
@@ -74,11 +74,11 @@ def SmithDiagonalGPU(seq1: Bytes, seq2: Bytes, n: Optional[int] = None, m: Optio
 
 
 def score(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0, rows: int = 0,
-          config: int = 0, ctas: int = 0, no_linear: bool = False, orient: int = 0, rebase: int = 0) -> int:
+          config: int = 0, ctas: int = 0, no_linear: bool = False, orient: int = 0, rebase: int = 0, two_sided: int = 0) -> int:
     """Gotoh local-alignment score of two HOST byte sequences with runtime parameters (swb200_score_ex)."""
     a, b = _u8(seq1), _u8(seq2)
     out = C.c_int(0)
-    p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, orient, rebase)
+    p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, orient, rebase, two_sided)
     rc = _lib.load().swb200_score_ex(_ptr(a), len(a), _ptr(b), len(b), C.byref(p), C.byref(o), C.byref(out))
     if rc != 0:
         raise SwbError(rc, "swb200_score_ex")
@@ -116,10 +116,10 @@ class Context:
 
     def score_device(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *,
                      stream: int = 0, lanes: int = 0, rows: int = 0, config: int = 0, ctas: int = 0,
-                     no_linear: bool = False, orient: int = 0, rebase: int = 0) -> int:
+                     no_linear: bool = False, orient: int = 0, rebase: int = 0, two_sided: int = 0) -> int:
         """d_seq1/d_seq2: device addresses of raw bytes (e.g. torch_tensor.data_ptr()); stream: cudaStream_t."""
         out = C.c_int(0)
-        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, orient, rebase)
+        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, orient, rebase, two_sided)
         rc = _lib.load().swb200_score_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
                                              C.byref(o), C.c_void_p(stream), C.byref(out))
         if rc != 0:

@@ -100,6 +100,56 @@ __global__ void encode_t_kernel(const uint8_t* __restrict__ src, long long n, ui
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status + 1, swb::STATUS_BAD_SYMBOL);
 }
 
+// Two-sided sweep, second half: Q' = pad rows + reverse(seq[mid..n)), one code byte per symbol.
+__global__ void encode_q_rev_kernel(const uint8_t* __restrict__ src, long long n, long long mid, long long pad,
+                                    uint8_t* __restrict__ dst, const uint8_t* __restrict__ lut, int* status) {
+  int bad = 0;
+  const long long total = pad + (n - mid);
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+    dst[k] = k < pad ? (uint8_t)4 : (uint8_t)code_of(src[n - 1 - (k - pad)], lut, bad);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status + 1, swb::STATUS_BAD_SYMBOL);
+}
+
+// Two-sided sweep, second half: T' = reverse(seq), 2-bit packed.
+__global__ void encode_t_rev_kernel(const uint8_t* __restrict__ src, long long n, uint64_t* __restrict__ dst,
+                                    const uint8_t* __restrict__ lut, int* status) {
+  int bad = 0;
+  const long long nwords = (n + 31) / 32;
+  for (long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x; wi < nwords; wi += (long long)gridDim.x * blockDim.x) {
+    uint64_t out = 0;
+    for (int k = 0; k < 32 && wi * 32 + k < n; ++k) out |= (uint64_t)code_of(src[n - 1 - (wi * 32 + k)], lut, bad) << (2 * k);
+    dst[wi] = out;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status + 1, swb::STATUS_BAD_SYMBOL);
+}
+
+// Two-sided sweep: alignments that cross the middle row.  f0[p + skew] = bottom boundary (H-open, F) of the forward
+// half at T position p; f1[p' + skew] = the same of the reversed half at reversed position p'.  A crossing path
+// passes lattice point (mid, x): best score ending there (forward) + best score starting there (reversed); a
+// vertical gap that straddles the row was opened twice, hence the + gap_init - gap_ext variant (Myers-Miller).
+__global__ void combine_two_sided_kernel(const uint2* __restrict__ f0, const uint2* __restrict__ f1, long long LT, int skew,
+                                         int linear, int gap_init, int gap_ext, int* result) {
+  int best = 0;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x <= LT; x += (long long)gridDim.x * blockDim.x) {
+    int Hf = 0, Ff = -1000000, Hb = 0, Fb = -1000000;
+    if (x >= 1) {
+      const uint32_t e = f0[x - 1 + skew].x;
+      if (linear) Hf = (int)(short)(e >> 16) + gap_init;
+      else { Hf = (int)(short)(e & 0xFFFFu) + gap_init; Ff = (int)(short)(e >> 16); }
+    }
+    if (x <= LT - 1) {
+      const uint32_t e = f1[(LT - 1 - x) + skew].x;
+      if (linear) Hb = (int)(short)(e >> 16) + gap_init;
+      else { Hb = (int)(short)(e & 0xFFFFu) + gap_init; Fb = (int)(short)(e >> 16); }
+    }
+    int v = Hf + Hb;
+    if (!linear) v = max(v, Ff + Fb + gap_init - gap_ext);
+    best = max(best, v);
+  }
+  best = __reduce_max_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(result, best);
+}
+
 // 256-bit presence map of the byte values in a buffer.
 __global__ void presence_kernel(const uint8_t* __restrict__ src, long long n, uint32_t* bitmap) {
   __shared__ uint32_t local[8];
@@ -128,6 +178,9 @@ struct swb200_ctx {
   uint8_t* d_ascii = nullptr; size_t ascii_cap = 0;
   uint8_t* d_q = nullptr; size_t q_cap = 0;
   uint64_t* d_t = nullptr; size_t t_cap = 0;     // words
+  uint8_t* d_q2 = nullptr; size_t q2_cap = 0;    // two-sided sweep: reversed second half
+  uint64_t* d_t2 = nullptr; size_t t2_cap = 0;
+  uint2* d_final = nullptr; size_t final_cap = 0; // two-sided sweep: the two middle boundary rows
   uint2* d_links = nullptr; size_t links_cap = 0;  // entries
   uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
   unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
@@ -215,6 +268,7 @@ struct Plan {
   int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine, 3/4 = 0/1 with re-based lanes
   int R, config, ctas;
   bool swap;     // Q = seq2 instead of seq1
+  bool two_sided;  // forward sweep over the top half of the rows + reversed sweep over the bottom half
 };
 
 // Estimated cycles for one (R, config) choice.  Model and constants fitted to B200 sweeps
@@ -223,7 +277,7 @@ struct Plan {
 // warps share a scheduler; a band starts `lag` steps after the band above it (lane skew + 64 steps of
 // poll look-ahead + ~60 steps of L2 visibility); the pair is done when the last band is.
 // The estimate only steers the choice of kernel, never the result.
-double estimate(long long LQ, long long LT, int mode, int R, int config, int sms) {
+double estimate(long long LQ, long long LT, int mode, int R, int config, int sms, bool two_sided = false) {
   const int rpb = swb::rows_per_band(R, mode);
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
@@ -234,12 +288,19 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
   const double lag = skew + 64 + 60;
+  if (two_sided) {            // each half has half the bands and half the warps
+    const long long NBh = (NB + 1) / 2, Wh = std::max<long long>(W / 2, 1);
+    const long long b = NBh - 1, w = b % Wh, r = b / Wh;
+    const double start = std::max((double)w * lag + (double)r * (double)(LT + skew), (double)b * lag);
+    return (start + (double)(LT + skew)) * cyc_step + 30000.0;      // + the combination kernel
+  }
   const long long b = NB - 1, w = b % W, r = b / W;
   const double start = std::max((double)w * lag + (double)r * (double)(LT + skew), (double)b * lag);
   return (start + (double)(LT + skew)) * cyc_step;
 }
 
-Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms) {
+Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms,
+               bool allow_two_sided = false) {
   Plan pl{};
   pl.swap = o.orient ? o.orient == 2 : m > n;   // default: stripe the longer sequence across lanes
   const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
@@ -253,7 +314,12 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
       const int R = swb::kRowChoices[ri];
       if (o.rows && o.rows != R) continue;
       const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
-      if (e < best) { best = e; pl.R = R; pl.config = ci; }
+      if (e < best) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
+      // two-sided: only plain 16-bit lanes, at least 4 bands per half
+      if (allow_two_sided && pl.mode <= 1 && o.two_sided >= 0 && LQ >= 8LL * swb::rows_per_band(R, pl.mode)) {
+        const double e2 = estimate(LQ, LT, pl.mode, R, ci, sms, true);
+        if (e2 < 0.97 * best || (o.two_sided > 0 && (e2 < best || !pl.two_sided))) { best = std::min(best, e2); pl.R = R; pl.config = ci; pl.two_sided = true; }
+      }
     }
   }
   if (best == 1e300) { pl.R = o.rows ? o.rows : 4; pl.config = o.config ? o.config : 1; }
@@ -287,7 +353,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
              const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
              int* score, int* status, const RingCfg* ring = nullptr) {
   const int world = ring ? ring->world : 1;
-  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world);
+  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr);
   const void* kern = kernel_for(pl);
   if (!kern) return fail(SWB200_ERR_ARG, "no kernel for rows=" + std::to_string(pl.R));
   const uint8_t* dq = pl.swap ? d_seq2 : d_seq1;
@@ -300,15 +366,23 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     return fail(SWB200_ERR_ARG, "re-based lanes are not safe for these scoring parameters / row count");
   if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
   if (ring && NB > 1 && ring->call_epoch == 0) return fail(SWB200_ERR_ARG, "ring epoch exhausted; create a new ring");
+  // two-sided sweep: rows [0, mid) forward, rows [mid, LQ) reversed (with pad rows in front so that the reversed
+  // half also ends exactly on a band boundary); mid is a multiple of the band height
+  const bool ts = pl.two_sided;
+  const long long NB0 = ts ? NB / 2 : NB;
+  const long long mid = NB0 * rpb;
+  const long long LQ1 = ts ? LQ - mid : 0, NB1 = ts ? (LQ1 + rpb - 1) / rpb : 0, pad1 = NB1 * rpb - LQ1;
 
   int per_sm = 0;
   SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, 0));
   if (per_sm < 1) return fail(SWB200_ERR_CUDA, "engine kernel does not fit on an SM");
-  long long ctas = std::min<long long>((NB + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
+  const long long want_warps = ts ? 2 * std::max(NB0, NB1) : NB;
+  long long ctas = std::min<long long>((want_warps + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
   if (pl.ctas > 0) ctas = std::min<long long>(ctas, pl.ctas);
-  ctas = std::max<long long>(ctas, 1);
+  ctas = std::max<long long>(ctas, ts ? 2 : 1);
   if (ring) ctas = pl.ctas > 0 ? std::min<long long>(pl.ctas, c->sms) : c->sms;   // every rank launches the same shape
   const int warps = (int)ctas * wpc;
+  const int split = ts ? warps / 2 : 0;
 
   const int skew = pl.mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
   const int align = pl.mode >= 3 ? swb::kRebaseBlock : swb::kChunk;
@@ -322,16 +396,19 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   int rc;
   if ((rc = grow(c->d_q, c->q_cap, (size_t)LQ + 64, false, s))) return rc;
   if ((rc = grow(c->d_t, c->t_cap, (size_t)(LT / 32 + 8), false, s))) return rc;
-  const size_t links_need = (size_t)std::max(warps - 1, 1) * 2 * (size_t)link_len;
-  const size_t ext_need = 2 * (size_t)ext_len;
-  const bool links_fresh = links_need > c->links_cap, ext_fresh = ext_need > c->ext_cap;
+  if (ts) {
+    if ((rc = grow(c->d_q2, c->q2_cap, (size_t)(NB1 * rpb) + 64, false, s))) return rc;
+    if ((rc = grow(c->d_t2, c->t2_cap, (size_t)(LT / 32 + 8), false, s))) return rc;
+    if ((rc = grow(c->d_final, c->final_cap, 4 * (size_t)ext_len, false, s))) return rc;
+  }
+  const size_t links_need = (size_t)std::max(warps, 1) * 2 * (size_t)link_len;
+  const size_t ext_need = (ts ? 4 : 2) * (size_t)ext_len;
   if ((rc = grow(c->d_links, c->links_cap, links_need, true, s))) return rc;
   if (ring) {
-    if (ext_need > ring->inbound_entries)
+    if (2 * (size_t)ext_len > ring->inbound_entries)
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
   } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
-  if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 2, false, s))) return rc;
-  (void)links_fresh; (void)ext_fresh;
+  if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 4, false, s))) return rc;
 
   // tags carry a 6-bit epoch; when it wraps, forget every old tag
   c->epoch += 1;
@@ -340,19 +417,28 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     SWB_CUDA(cudaMemsetAsync(c->d_links, 0, c->links_cap * sizeof(uint2), s));
     if (c->d_ext) SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
   }
-  SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 2) * sizeof(unsigned long long), s));
+  SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
   encode_q_kernel<<<eb, 256, 0, s>>>(dq, LQ, c->d_q, d_lut, c->d_result);
   const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
   encode_t_kernel<<<tb, 256, 0, s>>>(dt, LT, c->d_t, d_lut, c->d_result);
-  SWB_CUDA(cudaGetLastError());
   c->info.aux_launches += 2;
+  if (ts) {
+    const int eb2 = (int)std::min<long long>(std::max<long long>((NB1 * rpb) / 256, 1), 4LL * c->sms);
+    encode_q_rev_kernel<<<eb2, 256, 0, s>>>(dq, LQ, mid, pad1, c->d_q2, d_lut, c->d_result);
+    encode_t_rev_kernel<<<tb, 256, 0, s>>>(dt, LT, c->d_t2, d_lut, c->d_result);
+    c->info.aux_launches += 2;
+  }
+  SWB_CUDA(cudaGetLastError());
 
-  swb::EngineParams P{};
-  P.q_codes = c->d_q; P.t_packed = c->d_t; P.LQ = LQ; P.LT = LT; P.NB = (int)NB;
-  P.ring_total = warps * world; P.ring_offset = ring ? ring->rank * warps : 0; P.warps_local = warps;
+  const size_t ring_stride = 2 * (size_t)link_len;
+  swb::EngineLaunch L{};
+  swb::EngineParams& P = L.a;
+  P.q_codes = c->d_q; P.t_packed = c->d_t; P.LQ = ts ? mid : LQ; P.LT = LT; P.NB = (int)NB0;
+  const int warps0 = ts ? split : warps;
+  P.ring_total = warps0 * world; P.ring_offset = ring ? ring->rank * warps : 0; P.warps_local = warps0;
   P.links = c->d_links; P.link_mask = (unsigned)(link_len - 1); P.link_shift = link_shift;
   P.progress = c->d_progress;
   P.ext_in = ring ? ring->inbound : c->d_ext; P.ext_out = ring ? ring->next_inbound : c->d_ext;
@@ -368,9 +454,27 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     SWB_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)warps * 4 * sizeof(long long), s));
   }
   P.prof = d_prof;
-  void* args[] = {&P};
+  L.split = split;
+  if (ts) {
+    P.final_out = c->d_final; P.final_mask = (unsigned)(ext_len - 1);
+    swb::EngineParams& B = L.b;
+    B = P;
+    B.q_codes = c->d_q2; B.t_packed = c->d_t2; B.LQ = NB1 * rpb; B.NB = (int)NB1;
+    B.warps_local = warps - split; B.ring_total = warps - split; B.ring_offset = 0;
+    B.links = c->d_links + (size_t)split * ring_stride;
+    B.progress = c->d_progress + split + 2;
+    B.ext_in = c->d_ext + 2 * (size_t)ext_len; B.ext_out = c->d_ext + 2 * (size_t)ext_len;
+    B.final_out = c->d_final + 2 * (size_t)ext_len;
+    B.prof = d_prof ? d_prof + 4 * (size_t)split : nullptr;
+  }
+  void* args[] = {&L};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
+  if (ts) {
+    combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(c->d_final, c->d_final + 2 * (size_t)ext_len, LT, skew, pl.mode == 1,
+                                                        p.gap_init, p.gap_ext, c->d_result);
+    c->info.aux_launches += 1;
+  }
   SWB_CUDA(cudaEventRecord(c->ev1, s));
   SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 10 * sizeof(int), cudaMemcpyDeviceToHost, s));
   SWB_CUDA(cudaStreamSynchronize(s));
@@ -378,6 +482,15 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   *score = c->h_result[0];
   *status = c->h_result[1];
+  if (ts && getenv("SWB200_DUMP_FINAL")) {          // debugging aid: the two middle boundary rows as the kernels wrote them
+    std::vector<uint2> h(4 * (size_t)ext_len);
+    cudaMemcpy(h.data(), c->d_final, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("SWB200_DUMP_FINAL"), "wb");
+    if (f) {
+      long long hdr[6] = {LT, skew, ext_len, mid, pad1, (long long)pl.swap};
+      fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(uint2), h.size(), f); fclose(f);
+    }
+  }
   if (d_prof) {
     std::vector<long long> hp((size_t)warps * 4);
     cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -388,10 +501,11 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
               hp[4 * wv + 3] ? (double)hp[4 * wv + 2] / hp[4 * wv + 3] : 0.0, hp[4 * wv + 3]);
   }
   if ((*status & swb::STATUS_SPIN_TIMEOUT) && getenv("SWB200_DEBUG"))
-    fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u]\n",
+    fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u ts=%d]\n",
             c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
-            c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch);
+            c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch, (int)ts);
   c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.rebased = pl.mode >= 3; c->info.linear = pl.mode == 1 || pl.mode == 4;
+  c->info.two_sided = ts;
   c->info.rows = pl.R; c->info.config = pl.config;
   c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
   c->info.engine_ms = ms;
@@ -541,7 +655,7 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
 void swb200_ctx_destroy(swb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_links); cudaFree(c->d_ext);
+  cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
   cudaFree(c->d_progress); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);

@@ -51,6 +51,8 @@ struct EngineParams {
   uint2* ext_out;               // stream produced by the last local warp (peer memory on multi-GPU)
   unsigned ext_mask;
   int ext_shift;
+  uint2* final_out;             // optional: the LAST band's bottom boundary row goes here, slot = its step (two-sided sweep)
+  unsigned final_mask;
   uint32_t tag_base;            // local rings: epoch << 26
   uint32_t ext_tag_base;        // ext streams: 14-bit call epoch, high 6 bits << 26 | low 8 bits (ext lap bits are always 0)
   int* result;                  // [0] best score (atomicMax), [1] status bits (atomicOr)
@@ -176,14 +178,15 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
     const bool zero_src = band == 0 || (P.dbg & 2);
-    const bool has_sink = band + 1 < P.NB;
+    const bool is_final = band == P.NB - 1 && P.final_out != nullptr;   // its bottom row is wanted by the caller
+    const bool has_sink = band + 1 < P.NB || is_final;
     const bool emit = has_sink && last_lane && !(P.dbg & 1);
-    const bool first_local = lw == 0, last_local = lw == P.warps_local - 1;
+    const bool first_local = lw == 0, last_local = lw == P.warps_local - 1 || is_final;   // "last": full-length stream, no back-pressure
     const uint2* in = first_local ? P.ext_in : P.links + (size_t)(lw - 1) * 2 * ((size_t)P.link_mask + 1);
     const unsigned in_mask = first_local ? P.ext_mask : P.link_mask;
     const int in_shift = first_local ? P.ext_shift : P.link_shift;
-    uint2* out = last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1);
-    const unsigned out_mask = last_local ? P.ext_mask : P.link_mask;
+    uint2* out = is_final ? P.final_out : (last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1));
+    const unsigned out_mask = is_final ? P.final_mask : (last_local ? P.ext_mask : P.link_mask);
     const int out_shift = last_local ? P.ext_shift : P.link_shift;
     const uint32_t in_tag = (first_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)band << 8);   // written by band-1 as (band-1)+1
     const uint32_t out_tag = (last_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)(band + 1) << 8);
@@ -241,6 +244,15 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       const long long j = in_base + SLACK + lane + SKEW;
       epref = ld_entry(in + (j & in_mask));
       if (RB) bpref = ld_entry(in_bases + ((j >> 8) & inb_mask));
+    }
+    if (SLACK && !zero_src) {
+      // With the slack step lane 0 consumes at step i what was shuffled at step i-1; nothing is shuffled before
+      // step 0, so the boundary value of T position 0 is handed to lane 0 here.  (Every band starts with base 0,
+      // so no translation is needed in re-based mode.)
+      const long long j0 = in_base + SKEW;
+      const uint32_t v0 = wait_entry(P, w, true, in + (j0 & in_mask), in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu),
+                                     ld_entry(in + (j0 & in_mask)), wt);
+      if (lane == 0) yold = v0;
     }
 
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
@@ -420,14 +432,15 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
     const bool zero_src = band == 0 || (P.dbg & 2);
-    const bool has_sink = band + 1 < P.NB;
+    const bool is_final = band == P.NB - 1 && P.final_out != nullptr;   // its bottom row is wanted by the caller
+    const bool has_sink = band + 1 < P.NB || is_final;
     const bool emit = has_sink && last_lane && !(P.dbg & 1);
-    const bool first_local = lw == 0, last_local = lw == P.warps_local - 1;
+    const bool first_local = lw == 0, last_local = lw == P.warps_local - 1 || is_final;   // "last": full-length stream, no back-pressure
     const uint2* in = first_local ? P.ext_in : P.links + (size_t)(lw - 1) * 2 * ((size_t)P.link_mask + 1);
     const unsigned in_mask = first_local ? P.ext_mask : P.link_mask;
     const int in_shift = first_local ? P.ext_shift : P.link_shift;
-    uint2* out = last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1);
-    const unsigned out_mask = last_local ? P.ext_mask : P.link_mask;
+    uint2* out = is_final ? P.final_out : (last_local ? P.ext_out : P.links + (size_t)lw * 2 * ((size_t)P.link_mask + 1));
+    const unsigned out_mask = is_final ? P.final_mask : (last_local ? P.ext_mask : P.link_mask);
     const int out_shift = last_local ? P.ext_shift : P.link_shift;
     const uint32_t in_tag = (first_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)band << 8);
     const uint32_t out_tag = (last_local ? P.ext_tag_base : P.tag_base) | ((uint32_t)(band + 1) << 8);
@@ -470,6 +483,13 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     if (!zero_src && SLACK + lane < LT) {
       eprefH = ld_entry(in + 2 * ((in_base + SLACK + lane + SKEW) & in_mask));
       eprefF = ld_entry(in + 2 * ((in_base + SLACK + lane + SKEW) & in_mask) + 1);
+    }
+    if (SLACK && !zero_src) {      // boundary value of T position 0 for lane 0 (see the 16-bit engine)
+      const long long j0 = in_base + SKEW;
+      const uint32_t tg0 = in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu);
+      const uint32_t h0 = wait_entry(P, w, true, in + 2 * (j0 & in_mask), tg0, ld_entry(in + 2 * (j0 & in_mask)), wt);
+      const uint32_t f0 = wait_entry(P, w, true, in + 2 * (j0 & in_mask) + 1, tg0, ld_entry(in + 2 * (j0 & in_mask) + 1), wt);
+      if (lane == 0) { yoldH = (int)h0; yoldF = (int)f0; }
     }
 
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {

@@ -23,13 +23,23 @@ const void* engine_kernel_mode2(int R, int config);
 const void* engine_kernel_mode3(int R, int config);
 const void* engine_kernel_mode4(int R, int config);
 
+// One launch can carry two independent sub-problems (two-sided sweep): warps [0, split) run `a`, the rest run `b`,
+// each as its own ring with its own buffers.  split == 0: everything runs `a`.
+struct EngineLaunch {
+  EngineParams a, b;
+  int split;
+};
+
 #ifdef __CUDACC__
 template <int R, int MODE, int SLACK, int WPC>
-__global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineParams P) {
+__global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineLaunch L) {
   __shared__ WarpSmem sm[WPC];
   WarpCtx w{(int)(threadIdx.x & 31)};
   const int wi = (int)(threadIdx.x >> 5);
-  const int lw = (int)blockIdx.x * WPC + wi;
+  const int lw_all = (int)blockIdx.x * WPC + wi;
+  const bool second = L.split > 0 && lw_all >= L.split;
+  const EngineParams& P = second ? L.b : L.a;
+  const int lw = second ? lw_all - L.split : lw_all;
   if constexpr (MODE == 2) engine_warp_s32<R, SLACK>(P, w, lw, &sm[wi]);
   else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true>(P, w, lw, &sm[wi]);
   else engine_warp_s16<R, MODE, SLACK>(P, w, lw, &sm[wi]);

@@ -45,7 +45,7 @@ typedef struct {
   int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
   int orient;      /* 0 auto (stripe the longer sequence across lanes), 1 = stripe seq1, 2 = stripe seq2 */
   int rebase;      /* 16-bit lanes relative to a moving base (scores beyond 32767 at the packed rate): 0 auto, 1 force, -1 never */
-  int reserved[1];
+  int two_sided;   /* forward sweep on the top half of the rows + reversed sweep on the bottom half: 0 auto, 1 force, -1 never */
 } swb200_options;
 
 /* Return codes (legacy names have no error channel: they print and abort instead). */
@@ -83,6 +83,7 @@ SWB200_API int swb200_score_device(swb200_ctx* ctx, const unsigned char* d_seq1,
 typedef struct {
   int lanes;            /* 16 or 32 */
   int rebased;          /* 1 if the 16-bit lanes were relative to a moving base */
+  int two_sided;        /* 1 if the pair was swept from both ends (two half problems + combination kernel) */
   int linear;           /* 1 if the gap_init == gap_ext kernel was used */
   int rows;             /* R */
   int config;

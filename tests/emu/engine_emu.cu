@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
 
   // ACGT -> 2-bit codes exactly as the product's encode kernel does: (c >> 1) & 3
   std::vector<uint8_t> q(LQ + 1);
-  for (long long k = 0; k < LQ; ++k) q[k] = (uint8_t)((qa[k] >> 1) & 3);
+  for (long long k = 0; k < LQ; ++k) q[k] = qa[k] == 'N' ? (uint8_t)4 : (uint8_t)((qa[k] >> 1) & 3);   // 'N' = a row that matches nothing
   std::vector<uint64_t> t((LT + 31) / 32 + 1, 0);
   for (long long k = 0; k < LT; ++k) t[k >> 5] |= (uint64_t)((ta[k] >> 1) & 3) << (2 * (k & 31));
 
@@ -107,6 +107,9 @@ int main(int argc, char** argv) {
     p.match = ma; p.mismatch = mi; p.gap_init = gi; p.gap_ext = ge;
     p.spin_limit = 200000000LL;
   }
+  // optional: the last band's bottom boundary row (what the two-sided sweep combines), dumped to $EMU_FINAL
+  std::vector<uint2> final_row((size_t)4 * ext_len, make_uint2(0, 0));
+  if (getenv("EMU_FINAL")) for (int g = 0; g < G; ++g) { P[g].final_out = final_row.data(); P[g].final_mask = (unsigned)(ext_len - 1); }
   std::vector<WarpShared> ws((size_t)G * W);
   std::vector<WarpSmem> sm((size_t)G * W);
   for (auto& x : ws) pthread_barrier_init(&x.bar, nullptr, 32);
@@ -117,6 +120,11 @@ int main(int argc, char** argv) {
         th.emplace_back(fn, &P[g], &ws[(size_t)g * W + w], l, w, &sm[(size_t)g * W + w]);
   for (auto& x : th) x.join();
   printf("score=%d status=%d bands=%d nsteps=%lld\n", result[0], result[1], NB, nsteps);
+  if (getenv("EMU_FINAL")) {
+    FILE* f = fopen(getenv("EMU_FINAL"), "wb");
+    long long hdr[2] = {LT, skew};
+    fwrite(hdr, sizeof hdr, 1, f); fwrite(final_row.data(), sizeof(uint2), final_row.size(), f); fclose(f);
+  }
   return 0;
 }
 #endif

@@ -58,6 +58,8 @@ def oracle():
         for name in ("oracle_gotoh_full", "oracle_gotoh_rolling", "oracle_lazy_smith", "oracle_linear_gap"):
             getattr(lib, name).argtypes = sig
             getattr(lib, name).restype = C.c_int
+        lib.oracle_gotoh_last_row.argtypes = sig + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.oracle_gotoh_last_row.restype = C.c_int
         lib.oracle_gotoh_mt.argtypes = sig + [C.c_int]
         lib.oracle_gotoh_mt.restype = C.c_int
         lib.oracle_gotoh_banded.argtypes = sig[:4] + [C.c_int, C.c_int, C.POINTER(OracleParams), C.POINTER(C.c_int64)]
@@ -100,6 +102,17 @@ def lazy_smith(s1, s2, p=DEFAULT):
 
 def linear_gap(s1, s2, p=DEFAULT):
     return _call("oracle_linear_gap", s1, s2, p)
+
+
+def gotoh_last_row(s1, s2, p=DEFAULT):
+    """(best, H[m][0..n], F[m][0..n]): columns index seq1, the row is the last row of seq2."""
+    a, b = _u8(s1), _u8(s2)
+    pp = _params(p)
+    H = np.zeros(len(a) + 1, dtype=np.int32)
+    F = np.zeros(len(a) + 1, dtype=np.int32)
+    best = oracle().oracle_gotoh_last_row(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), H.ctypes.data_as(C.POINTER(C.c_int)),
+                                          F.ctypes.data_as(C.POINTER(C.c_int)))
+    return best, H, F
 
 
 def gotoh_mt(s1, s2, p=DEFAULT, threads=0):

@@ -2,6 +2,7 @@
 with the oracle.  This is how the hand-off protocol (tags, ring laps, back-pressure, ring
 wrap-around over several rounds, multi-GPU ring) is covered without a GPU; the same source is what
 the sm_100a kernels compile.  Needs nvcc (host compile only)."""
+import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -26,14 +27,23 @@ def emu():
         subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(EMU),
                         str(src), "-lpthread"], check=True, cwd=EMU_DIR)
 
-    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp")):
-        qf, tf = tmp / "swb_emu_q.bin", tmp / "swb_emu_t.bin"
+    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp"), final_row=False):
+        qf, tf, ff = tmp / "swb_emu_q.bin", tmp / "swb_emu_t.bin", tmp / "swb_emu_final.bin"
         qf.write_bytes(bytes(q)); tf.write_bytes(bytes(t))
         ma, mi, gi, ge = p
+        env = dict(os.environ, EMU_FINAL=str(ff)) if final_row else dict(os.environ)
+        env.pop("EMU_FINAL", None) if not final_row else None
         out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],
-                             capture_output=True, text=True, timeout=900, check=True).stdout
+                             capture_output=True, text=True, timeout=900, check=True, env=env).stdout
         d = dict(kv.split("=") for kv in out.split())
-        return int(d["score"]), int(d["status"])
+        if not final_row:
+            return int(d["score"]), int(d["status"])
+        raw = ff.read_bytes()
+        LT, skew = (int(x) for x in np.frombuffer(raw[:16], dtype=np.int64))
+        ent = np.frombuffer(raw[16:], dtype=np.uint32).reshape(-1, 2)[:, 0][skew:skew + LT]
+        lo = (ent & 0xFFFF).astype(np.int16).astype(np.int32)
+        hi = (ent >> 16).astype(np.int16).astype(np.int32)
+        return int(d["score"]), int(d["status"]), lo, hi
     return run
 
 
@@ -88,3 +98,22 @@ def test_s16_overflow_is_flagged(emu):
     score, status = emu(a, a, 1, 0, 1, 1, 1, p=(100, -1, 1, 1))
     assert status & 1
     assert emu(a, a, 1, 2, 1, 1, 1, p=(100, -1, 1, 1)) == (100 * 328, 0)
+
+
+@pytest.mark.parametrize("mode,slack", [(0, 1), (0, 0), (1, 1), (1, 0)])
+def test_bottom_boundary_row_of_the_last_band(emu, mode, slack):
+    """Stronger than the score: the whole bottom boundary row (H and, affine mode, F at every T position) after
+    4 bands must equal the last DP row of the oracle.  Scoring with positive drift (cheap gaps) makes every cell
+    matter; this is the check that exposed a missing hand-off of T position 0 with the slack step."""
+    p = (3, -2, 2, 2) if mode == 1 else (3, -2, 3, 1)
+    for seed in (2010, 2011):
+        q = rng.random_acgt(seed, 0, 256)          # 4 bands of 64 rows (R = 1), no padding rows
+        t = rng.random_acgt(seed, 1, 300)
+        best, H, F = O.gotoh_last_row(t, q, p)     # columns = T positions, last row = last Q row
+        score, status, lo, hi = emu(q, t, 1, mode, slack, 3, 1, p, final_row=True)
+        assert (score, status) == (best, 0)
+        gH = (hi if mode == 1 else lo) + p[2]      # entries carry H - gap_init
+        assert gH.tolist() == H[1:].tolist()
+        if mode == 0:
+            pos = (F[1:] > 0) | (hi > 0)           # non-positive F never matters and conventions differ at the border
+            assert hi[pos].tolist() == F[1:][pos].tolist()

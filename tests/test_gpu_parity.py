@@ -70,7 +70,7 @@ def test_reference_fixture_scores_other_params(api):
 def test_every_kernel_variant_against_oracle(api, config, lanes, no_linear):
     a, b = planted(500, 3000)
     c, d = rng.random_acgt(501, 0, 2100), rng.random_acgt(501, 1, 5000)
-    for p in (O.DEFAULT, (2, -3, 5, 1)):
+    for p in (O.DEFAULT, (2, -3, 5, 1), (3, -2, 2, 2), (3, -2, 3, 1)):     # the last two: positive drift, every cell matters
         if p[2] != p[3] and not no_linear:
             continue
         w1, w2 = O.gotoh_rolling(a, b, p), O.gotoh_rolling(c, d, p)
@@ -109,13 +109,14 @@ def test_other_alphabets_are_remapped(api):
 def test_scores_beyond_the_s16_range_rerun_in_32_bit(api):
     a = rng.random_acgt(520, 0, 40000)
     assert api.score(a, a) == 40000                      # analytic: identical sequences score MATCH*N
+    assert api.score(a, a, two_sided=-1) == 40000
     info = api.last_run()                                # plain 16-bit lanes reported the overflow, re-based lanes finished the job
     assert info["lanes"] == 16 and info["rebased"] == 1 and info["engine_launches"] == 2
-    assert api.score(a, a, rebase=-1) == 40000 and api.last_run()["lanes"] == 32
+    assert api.score(a, a, rebase=-1, two_sided=-1) == 40000 and api.last_run()["lanes"] == 32
     b = a.copy(); b[20000:20010] = np.where(b[20000:20010] == ord('A'), ord('C'), ord('A'))   # 10 substituted bases
     assert api.score(a, b) == O.gotoh_mt(a, b)
     with pytest.raises(api.SwbError) as e:
-        api.score(a, a, lanes=16, rebase=-1)
+        api.score(a, a, lanes=16, rebase=-1, two_sided=-1)
     assert e.value.code == -6
 
 
@@ -280,3 +281,31 @@ def test_rebased_lanes_refuse_unsafe_parameters(api):
     with pytest.raises(api.SwbError):
         api.score(a, a, (100, -100, 20, 20), lanes=16, rebase=1, rows=8)      # steps of 120 per cell: no safe base spacing
     assert api.score(a, a, (100, -100, 20, 20)) == 500000                     # automatic policy falls back to 32 bit
+
+
+def test_two_sided_sweep_against_oracle(api):
+    """Forward sweep over the top half of the rows, reversed sweep over the bottom half, combination at the middle
+    row: alignments that lie in one half, cross the middle diagonally, or cross it inside a vertical gap."""
+    n = 6000
+    a = rng.random_acgt(900, 0, n)
+    cases = {
+        "random": rng.random_acgt(900, 1, n),
+        "similar (crosses the middle)": rng.mutate(a, 900, 2, 0.05, 0.02),
+        "top half only": np.concatenate([a[:2500], rng.random_acgt(900, 3, 3500)]),
+        "bottom half only": np.concatenate([rng.random_acgt(900, 4, 3500), a[3500:]]),
+        "gap straddling the middle": np.concatenate([a[:2990], a[3030:]]),     # 40 bases of a missing around the middle
+        "insertion at the middle": np.concatenate([a[:3000], rng.random_acgt(900, 5, 25), a[3000:]]),
+    }
+    for name, b in cases.items():
+        for p in (O.DEFAULT, (2, -3, 5, 1), (3, -2, 2, 2), (1, -1, 4, 2)):
+            want = O.gotoh_mt(a, b, p)
+            for rows, config in ((1, 1), (2, 3), (4, 2)):
+                for no_linear in (False, True):
+                    got = api.score(a, b, p, rows=rows, config=config, no_linear=no_linear, two_sided=1)
+                    assert api.last_run()["two_sided"] == 1
+                    assert got == want, (name, p, rows, config, no_linear, got, want)
+                    assert api.score(b, a, p, rows=rows, config=config, no_linear=no_linear, two_sided=1) == want
+    # the middle need not be the middle of the alignment: very unequal lengths, striped sequence chosen by orient
+    b = rng.mutate(a[1000:1700], 901, 1, 0.03, 0.01)
+    assert api.score(a, b, two_sided=1, rows=1) == O.gotoh_rolling(a, b)
+    assert api.score(a, b, two_sided=1, rows=2, orient=1) == O.gotoh_rolling(a, b)
