@@ -282,8 +282,8 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
-  const int skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : (mode == 2 ? 12.5 : (mode == 3 ? 15.0 : 11.0)));
+  const int skew = (mode == 2 || mode == 5) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : (mode == 2 ? 12.5 : (mode == 3 ? 15.0 : (mode == 4 ? 11.0 : 14.5))));
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
@@ -307,6 +307,7 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   // lanes: 16 = packed s16, 17 = packed s16 re-based, 32 = s32
   pl.mode = lanes == 32 ? 2 : ((p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0);
   if (lanes == 17) pl.mode += 3;
+  if (lanes == 33) pl.mode = 5;          // 32-bit lanes, any byte alphabet
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
@@ -333,7 +334,8 @@ const void* kernel_for(const Plan& pl) {
     case 1: return swb::engine_kernel_mode1(pl.R, pl.config);
     case 2: return swb::engine_kernel_mode2(pl.R, pl.config);
     case 3: return swb::engine_kernel_mode3(pl.R, pl.config);
-    default: return swb::engine_kernel_mode4(pl.R, pl.config);
+    case 4: return swb::engine_kernel_mode4(pl.R, pl.config);
+    default: return swb::engine_kernel_mode5(pl.R, pl.config);
   }
 }
 
@@ -362,7 +364,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int wpc = swb::config_wpc(pl.config), slack = swb::config_slack(pl.config);
   const int rpb = swb::rows_per_band(pl.R, pl.mode);
   const long long NB = (LQ + rpb - 1) / rpb;
-  if (pl.mode >= 3 && !rebase_is_safe(p, pl.R))
+  if ((pl.mode == 3 || pl.mode == 4) && !rebase_is_safe(p, pl.R))
     return fail(SWB200_ERR_ARG, "re-based lanes are not safe for these scoring parameters / row count");
   if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
   if (ring && NB > 1 && ring->call_epoch == 0) return fail(SWB200_ERR_ARG, "ring epoch exhausted; create a new ring");
@@ -384,8 +386,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int warps = (int)ctas * wpc;
   const int split = ts ? warps / 2 : 0;
 
-  const int skew = pl.mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const int align = pl.mode >= 3 ? swb::kRebaseBlock : swb::kChunk;
+  const int skew = (pl.mode == 2 || pl.mode == 5) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const int align = (pl.mode == 3 || pl.mode == 4) ? swb::kRebaseBlock : swb::kChunk;
   const long long nsteps = ((LT + skew + align - 1) / align) * align;
   const int ext_shift = std::max(4, log2_ceil(nsteps + swb::kChunk));
   const long long ext_len = 1LL << ext_shift;
@@ -420,11 +422,14 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
+  const bool generic = pl.mode == 5;       // raw bytes straight from the caller's buffers, nothing to encode
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
-  encode_q_kernel<<<eb, 256, 0, s>>>(dq, LQ, c->d_q, d_lut, c->d_result);
   const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
-  encode_t_kernel<<<tb, 256, 0, s>>>(dt, LT, c->d_t, d_lut, c->d_result);
-  c->info.aux_launches += 2;
+  if (!generic) {
+    encode_q_kernel<<<eb, 256, 0, s>>>(dq, LQ, c->d_q, d_lut, c->d_result);
+    encode_t_kernel<<<tb, 256, 0, s>>>(dt, LT, c->d_t, d_lut, c->d_result);
+    c->info.aux_launches += 2;
+  }
   if (ts) {
     const int eb2 = (int)std::min<long long>(std::max<long long>((NB1 * rpb) / 256, 1), 4LL * c->sms);
     encode_q_rev_kernel<<<eb2, 256, 0, s>>>(dq, LQ, mid, pad1, c->d_q2, d_lut, c->d_result);
@@ -436,7 +441,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const size_t ring_stride = 2 * (size_t)link_len;
   swb::EngineLaunch L{};
   swb::EngineParams& P = L.a;
-  P.q_codes = c->d_q; P.t_packed = c->d_t; P.LQ = ts ? mid : LQ; P.LT = LT; P.NB = (int)NB0;
+  P.q_codes = generic ? dq : c->d_q; P.t_packed = c->d_t; P.t_bytes = dt; P.LQ = ts ? mid : LQ; P.LT = LT; P.NB = (int)NB0;
   const int warps0 = ts ? split : warps;
   P.ring_total = warps0 * world; P.ring_offset = ring ? ring->rank * warps : 0; P.warps_local = warps0;
   P.links = c->d_links; P.link_mask = (unsigned)(link_len - 1); P.link_shift = link_shift;
@@ -504,7 +509,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u ts=%d]\n",
             c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
             c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch, (int)ts);
-  c->info.lanes = pl.mode == 2 ? 32 : 16; c->info.rebased = pl.mode >= 3; c->info.linear = pl.mode == 1 || pl.mode == 4;
+  c->info.lanes = (pl.mode == 2 || pl.mode == 5) ? 32 : 16; c->info.rebased = pl.mode == 3 || pl.mode == 4;
+  c->info.linear = pl.mode == 1 || pl.mode == 4;
   c->info.two_sided = ts;
   c->info.rows = pl.R; c->info.config = pl.config;
   c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
@@ -542,7 +548,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
     int score = 0, status = 0;
     if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status))) return rc;
     if (status & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off timed out");
-    if (status & swb::STATUS_BAD_SYMBOL) {
+    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33) {
       if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
       // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
       SWB_CUDA(cudaMemsetAsync(c->d_result + 16, 0, 8 * sizeof(int), s));
@@ -559,8 +565,11 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
           if (distinct < 4) table[v] = (uint8_t)distinct;
           ++distinct;
         }
-      if (distinct > 4)
-        return fail(SWB200_ERR_ALPHABET, "more than 4 distinct byte values (" + std::to_string(distinct) + ")");
+      if (distinct > 4) {
+        // the reference compares raw bytes (main.cpp:28-33): score such pairs with the byte-compare kernel
+        lanes = 33;
+        continue;
+      }
       SWB_CUDA(cudaMemcpyAsync(c->d_lut, table, 256, cudaMemcpyHostToDevice, s));
       SWB_CUDA(cudaStreamSynchronize(s));
       lut = c->d_lut;

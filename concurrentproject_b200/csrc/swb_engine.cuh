@@ -36,8 +36,9 @@ constexpr int kRebaseBlock = 256;     // steps between re-base decisions (re-bas
 constexpr int kRebaseTrigger = 8000;  // re-centre when a live H-open leaves [-8000, 8000] relative to the base
 
 struct EngineParams {
-  const uint8_t* q_codes;       // LQ codes in {0,1,2,3}; >= 4 never matches
+  const uint8_t* q_codes;       // LQ codes in {0,1,2,3}; >= 4 never matches (generic-byte mode: the raw bytes)
   const uint64_t* t_packed;     // LT 2-bit codes, 32 per 64-bit word, position p at bits 2*(p%32)
+  const uint8_t* t_bytes;       // generic-byte mode only: the raw bytes of T
   long long LQ, LT;
   int NB;                       // bands = ceil(LQ / rows_per_band)
   int ring_total;               // warps in the whole ring (all GPUs)
@@ -414,7 +415,9 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 //  32-bit engine (scores beyond the s16 range): one sub-lane per thread, band = 32*R rows.
 //  Boundary entries come in pairs: slot 2j = H-open, slot 2j+1 = F.
 // =================================================================================================
-template <int R, int SLACK>
+//  GEN: any byte alphabet (the reference compares raw bytes, main.cpp:28-33): the table ring holds the raw T byte
+//  and the substitution score is a compare + select instead of a PRMT table look-up.
+template <int R, int SLACK, bool GEN = false>
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
@@ -423,8 +426,9 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
   const int src_lane = (lane + 31) & 31;
   const int nopen = -P.gap_init, next = -P.gap_ext;
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
-  const uint32_t padw = padb * 0x01010101u;
+  const uint32_t padw = GEN ? 0x200u : padb * 0x01010101u;       // GEN: 0x200 equals no byte and no pad row (0x100)
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
+  const int s_match = P.match + P.gap_init, s_mismatch = P.mismatch + P.gap_init;
   const long long LT = P.LT;
   const long long nsteps = ((LT + SKEW + kChunk - 1) / kChunk) * kChunk;
   int best0 = 0, best1 = 0;
@@ -458,7 +462,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const long long a = row0 + r;
-        sel[r] = mk_sel32(a < P.LQ ? P.q_codes[a] : 4u);
+        sel[r] = GEN ? (a < P.LQ ? (uint32_t)P.q_codes[a] : 0x100u) : mk_sel32(a < P.LQ ? P.q_codes[a] : 4u);
       }
     }
     int Ho[R], E[R];
@@ -472,13 +476,18 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     w.sync();
     {
       const long long q = lane;
-      uint32_t c = 4;
-      if (q < LT) c = (uint32_t)(P.t_packed[q >> 5] >> (2 * (q & 31))) & 3u;
-      const uint32_t tw = table_word(c, padw, flip);
+      uint32_t tw;
+      if (GEN) tw = q < LT ? (uint32_t)P.t_bytes[q] : padw;
+      else {
+        uint32_t c = 4;
+        if (q < LT) c = (uint32_t)(P.t_packed[q >> 5] >> (2 * (q & 31))) & 3u;
+        tw = table_word(c, padw, flip);
+      }
       sm->tab[q & (kTabRing - 1)] = tw;
       sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
     }
-    uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(P.t_packed + ((kChunk + lane) >> 5)) : 0ull;
+    uint64_t twpref = GEN ? (kChunk + lane < LT ? (uint64_t)P.t_bytes[kChunk + lane] : (uint64_t)padw)
+                          : ((kChunk + lane < LT) ? ld_early_u64(P.t_packed + ((kChunk + lane) >> 5)) : 0ull);
     uint2 eprefH = make_uint2(0u, 0u), eprefF = make_uint2(0u, 0u);
     if (!zero_src && SLACK + lane < LT) {
       eprefH = ld_entry(in + 2 * ((in_base + SLACK + lane + SKEW) & in_mask));
@@ -495,12 +504,17 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
       {
         const long long q = i0 + kChunk + lane;
-        uint32_t c = 4;
-        if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
-        const uint32_t tw = table_word(c, padw, flip);
+        uint32_t tw;
+        if (GEN) tw = (uint32_t)twpref;
+        else {
+          uint32_t c = 4;
+          if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
+          tw = table_word(c, padw, flip);
+        }
         sm->tab[q & (kTabRing - 1)] = tw;
         sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
-        twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
+        if (GEN) twpref = q + kChunk < LT ? (uint64_t)P.t_bytes[q + kChunk] : (uint64_t)padw;
+        else twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
       }
       {
         const long long q = i0 + SLACK + lane;
@@ -553,7 +567,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
         up_prev = upHo;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int s = (int)prmt(Tw, 0u, sel[r]);
+          const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
           const int d = diag + s;
           const int old = Ho[r];
           E[r] = addmax32(E[r], next, old);
@@ -579,6 +593,6 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 }
 
 // rows of Q one band covers
-SWB_HD int rows_per_band(int R, int mode) { return (mode == 2 ? 32 : 64) * R; }
+SWB_HD int rows_per_band(int R, int mode) { return ((mode == 2 || mode == 5) ? 32 : 64) * R; }
 
 }  // namespace swb

@@ -22,6 +22,7 @@ const void* engine_kernel_mode1(int R, int config);
 const void* engine_kernel_mode2(int R, int config);
 const void* engine_kernel_mode3(int R, int config);
 const void* engine_kernel_mode4(int R, int config);
+const void* engine_kernel_mode5(int R, int config);   // s32, any byte alphabet (compare instead of table look-up)
 
 // One launch can carry two independent sub-problems (two-sided sweep): warps [0, split) run `a`, the rest run `b`,
 // each as its own ring with its own buffers.  split == 0: everything runs `a`.
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   const EngineParams& P = second ? L.b : L.a;
   const int lw = second ? lw_all - L.split : lw_all;
   if constexpr (MODE == 2) engine_warp_s32<R, SLACK>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 5) engine_warp_s32<R, SLACK, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true>(P, w, lw, &sm[wi]);
   else engine_warp_s16<R, MODE, SLACK>(P, w, lw, &sm[wi]);
 }

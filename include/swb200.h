@@ -52,7 +52,7 @@ typedef struct {
 #define SWB200_OK 0
 #define SWB200_ERR_CUDA (-1)      /* a CUDA call failed; see swb200_last_error() */
 #define SWB200_ERR_ARG (-2)       /* bad argument or parameter outside the documented limits */
-#define SWB200_ERR_ALPHABET (-3)  /* more than 4 distinct byte values in the two sequences */
+#define SWB200_ERR_ALPHABET (-3)  /* batch calls only: a byte other than A,C,G,T */
 #define SWB200_ERR_TIMEOUT (-4)   /* a boundary hand-off never arrived (peer GPU gone) */
 #define SWB200_ERR_NOMEM (-5)
 #define SWB200_ERR_RANGE (-6)     /* score does not fit the requested lane width */

@@ -27,17 +27,21 @@ def planted(seed, n, sub=0.06, indel=0.03):
 
 def test_known_answer_tables_through_legacy_names(api):
     for c in load_json("kat.json"):
-        distinct = len(set(c["seq1"]) | set(c["seq2"]))
         for name in LEGACY:
-            if distinct > 4:
-                continue
             assert getattr(api, name)(c["seq1"], c["seq2"]) == c["score"], (name, c["source"])
 
 
-def test_more_than_four_symbols_is_an_error_not_a_wrong_score(api):
-    with pytest.raises(api.SwbError) as e:
-        api.score("GATTACA", "GCATGCU")
-    assert e.value.code == -3
+def test_more_than_four_symbols_use_the_byte_compare_kernel(api):
+    # the reference compares raw bytes (main.cpp:28-33); mainMarta.cpp's GATTACA/GCATGCU has five symbols
+    assert api.score("GATTACA", "GCATGCU") == 2
+    assert api.last_run()["lanes"] == 32
+    r = np.random.default_rng(5)
+    for n, m, k in ((300, 500, 5), (2000, 1500, 20), (5000, 5000, 256)):
+        a = r.integers(0, k, n, dtype=np.uint8); b = r.integers(0, k, m, dtype=np.uint8)
+        b[m // 3: m // 3 + min(n, m) // 4] = a[: min(n, m) // 4]            # plant a common stretch
+        for p in (O.DEFAULT, (2, -3, 5, 1)):
+            assert api.score(a, b, p) == O.gotoh_rolling(a, b, p), (n, m, k, p)
+            assert api.score(b, a, p, rows=2, config=2) == O.gotoh_rolling(a, b, p)
 
 
 @pytest.mark.parametrize("L", [32, 516, 4096])
