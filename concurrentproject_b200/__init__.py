@@ -3,11 +3,11 @@ score-function entry points (algoGPU.h).  The product is concurrentproject_b200/
 (hand-written sm_100a CUDA, C ABI in include/); this package is its thin host-side mirror."""
 from . import rng  # noqa: F401  (pure numpy, safe without the CUDA library)
 
-__all__ = ["rng", "api"]
+__all__ = ["rng", "api", "fasta", "ring"]
 
 
 def __getattr__(name):
-    if name == "api":
+    if name in ("api", "fasta", "ring"):
         import importlib
-        return importlib.import_module(".api", __name__)
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

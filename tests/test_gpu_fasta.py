@@ -1,0 +1,60 @@
+"""FASTA input path on the GPU: ragged, length-bucketed batches against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from concurrentproject_b200 import rng
+
+pytestmark = pytest.mark.gpu
+
+
+def _ragged(seed, npairs, max_read, max_win, with_n=False):
+    r = np.random.default_rng(seed)
+    s1, s2 = [], []
+    for k in range(npairs):
+        wl = int(r.integers(0, max_win + 1))
+        w = rng.random_acgt(seed, 2 * k, wl)
+        rl = int(r.integers(0, max_read + 1))
+        if wl > 8 and k % 2 == 0:                       # a mutated piece of the window
+            o = int(r.integers(0, wl - min(rl, wl) + 1))
+            rd = rng.mutate(w[o:o + min(rl, wl)], seed, 2 * k + 1, 0.05, 0.02)
+        else:
+            rd = rng.random_acgt(seed, 2 * k + 1, rl)
+        if with_n and k % 17 == 3 and len(rd) > 2:
+            rd = rd[:1] + b"N" + rd[2:]
+        if k % 5 == 0:
+            w, rd = rd, w                               # the shorter one is not always first
+        s1.append(bytes(rd)); s2.append(bytes(w))
+    return s1, s2
+
+
+def test_score_pairs_ragged_lengths_match_oracle(tmp_path):
+    from concurrentproject_b200 import fasta
+    s1, s2 = _ragged(11, 3000, 300, 1200)
+    fasta.write_fasta(str(tmp_path / "a.fa"), [f"r{k}" for k in range(len(s1))], s1)
+    fasta.write_fasta(str(tmp_path / "b.fa"), [f"w{k}" for k in range(len(s2))], s2, width=77)
+    a, b = fasta.read_fasta(str(tmp_path / "a.fa")), fasta.read_fasta(str(tmp_path / "b.fa"))
+    want = O.gotoh_batch(s1, s2)
+    for mb in (1, 64, 100000):                          # one bucket per class ... everything merged into one
+        got = fasta.score_pairs(a, b, min_bucket=mb)
+        assert np.array_equal(got, want), mb
+    p = (2, -3, 4, 1)
+    assert np.array_equal(fasta.score_pairs(s1[:500], s2[:500], p, min_bucket=32), O.gotoh_batch(s1[:500], s2[:500], p))
+
+
+def test_score_pairs_routes_other_alphabets_and_long_pairs_to_the_pair_engine():
+    from concurrentproject_b200 import fasta
+    s1, s2 = _ragged(12, 400, 200, 600, with_n=True)
+    s1 += [rng.random_acgt(12, 9001, 1500), b"MKVLAAGIVGLLLAQWSHA", b""]
+    s2 += [rng.random_acgt(12, 9002, 2500), b"MKVLSAGIVALLLAQPSHA", b"ACGT"]
+    want = np.array([O.gotoh_rolling(x, y) for x, y in zip(s1, s2)], dtype=np.int32)
+    assert np.array_equal(fasta.score_pairs(s1, s2, min_bucket=16), want)
+
+
+def test_search_one_query_against_a_database():
+    from concurrentproject_b200 import fasta
+    db = [rng.random_acgt(13, k, 50 + (k * 37) % 900) for k in range(700)]
+    q = rng.mutate(db[123][10:160], 13, 5000, 0.04, 0.01)
+    want = np.array([O.gotoh_rolling(q, d) for d in db], dtype=np.int32)
+    got = fasta.search(q, db, min_bucket=64)
+    assert np.array_equal(got, want) and int(np.argmax(got)) == 123
