@@ -49,6 +49,8 @@ def mutate(seq: np.ndarray, seed: int, stream: int, sub_rate: float, indel_rate:
     Used for planted-similarity pairs (cfg4 reads, cfg5 long reads).  Decisions come from
     mix64(seed, stream, position) so the result is reproducible from (seed, stream) alone.
     """
+    if isinstance(seq, (bytes, bytearray)):
+        seq = np.frombuffer(bytes(seq), dtype=np.uint8)
     n = len(seq)
     if n == 0:
         return seq.copy()

@@ -20,11 +20,12 @@ def _ragged(seed, npairs, max_read, max_win, with_n=False):
             rd = rng.mutate(w[o:o + min(rl, wl)], seed, 2 * k + 1, 0.05, 0.02)
         else:
             rd = rng.random_acgt(seed, 2 * k + 1, rl)
+        w, rd = bytes(w), bytes(rd)
         if with_n and k % 17 == 3 and len(rd) > 2:
             rd = rd[:1] + b"N" + rd[2:]
         if k % 5 == 0:
             w, rd = rd, w                               # the shorter one is not always first
-        s1.append(bytes(rd)); s2.append(bytes(w))
+        s1.append(rd); s2.append(w)
     return s1, s2
 
 
@@ -45,15 +46,15 @@ def test_score_pairs_ragged_lengths_match_oracle(tmp_path):
 def test_score_pairs_routes_other_alphabets_and_long_pairs_to_the_pair_engine():
     from concurrentproject_b200 import fasta
     s1, s2 = _ragged(12, 400, 200, 600, with_n=True)
-    s1 += [rng.random_acgt(12, 9001, 1500), b"MKVLAAGIVGLLLAQWSHA", b""]
-    s2 += [rng.random_acgt(12, 9002, 2500), b"MKVLSAGIVALLLAQPSHA", b"ACGT"]
+    s1 += [bytes(rng.random_acgt(12, 9001, 1500)), b"MKVLAAGIVGLLLAQWSHA", b""]
+    s2 += [bytes(rng.random_acgt(12, 9002, 2500)), b"MKVLSAGIVALLLAQPSHA", b"ACGT"]
     want = np.array([O.gotoh_rolling(x, y) for x, y in zip(s1, s2)], dtype=np.int32)
     assert np.array_equal(fasta.score_pairs(s1, s2, min_bucket=16), want)
 
 
 def test_search_one_query_against_a_database():
     from concurrentproject_b200 import fasta
-    db = [rng.random_acgt(13, k, 50 + (k * 37) % 900) for k in range(700)]
+    db = [bytes(rng.random_acgt(13, k, 50 + (k * 37) % 900)) for k in range(700)]
     q = rng.mutate(db[123][10:160], 13, 5000, 0.04, 0.01)
     want = np.array([O.gotoh_rolling(q, d) for d in db], dtype=np.int32)
     got = fasta.search(q, db, min_bucket=64)
