@@ -20,6 +20,8 @@ def main():
     modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["lin", "aff", "s32"]
     reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
     ts = int(sys.argv[6]) if len(sys.argv) > 6 else 0        # two_sided option: 0 auto, 1 force, -1 never
+    rb = int(sys.argv[7]) if len(sys.argv) > 7 else 0        # rebase option: 0 auto, 1 force, -1 never
+    tag = sys.argv[8] if len(sys.argv) > 8 else ""
     mm = {"lin": (16, False), "aff": (16, True), "s32": (32, True)}
     ctx = api.Context(0)
     with open(out / "sweep.jsonl", "a") as f:
@@ -34,14 +36,14 @@ def main():
                         try:
                             for rep in range(reps):
                                 s = ctx.score_device(a.data_ptr(), n, b.data_ptr(), n, lanes=lanes, rows=rows, config=config,
-                                                     no_linear=no_linear, two_sided=ts)
+                                                     no_linear=no_linear, two_sided=ts, rebase=rb)
                                 info = ctx.last_run()
                                 ms = info["engine_ms"]
                                 best = ms if best is None else min(best, ms)
                         except Exception as e:
                             print("ERR", n, mode, config, rows, e, flush=True)
                             continue
-                        rec = {"n": n, "mode": mode, "ts": info["two_sided"], "rows": rows, "config": config, "ctas": info["ctas"], "bands": info["bands"],
+                        rec = {"tag": tag, "n": n, "mode": mode, "ts": info["two_sided"], "rb": info["rebased"], "rows": rows, "config": config, "ctas": info["ctas"], "bands": info["bands"],
                                "ms": round(best, 4), "gcups": round(n * n / best / 1e6, 1), "score": s}
                         f.write(json.dumps(rec) + "\n"); f.flush()
                         print(rec, flush=True)

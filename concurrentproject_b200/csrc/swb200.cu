@@ -272,18 +272,21 @@ struct Plan {
 };
 
 // Estimated cycles for one (R, config) choice.  Model and constants fitted to B200 sweeps
-// (profiles/r01_sweep_*.jsonl): a warp-step costs per_row*R + 39 cycles with one warp per scheduler
-// (14 / 10 / 12.5 cycles per row vector for s16 affine / s16 linear / s32), 1.5x that per warp when two
-// warps share a scheduler; a band starts `lag` steps after the band above it (lane skew + 64 steps of
-// poll look-ahead + ~60 steps of L2 visibility); the pair is done when the last band is.
-// The estimate only steers the choice of kernel, never the result.
+// (profiles/r01_sweep_*.jsonl): a warp-step costs per_row*R + 39 cycles.  With one warp per scheduler
+// (configs 1, 3: short-chain row loop) per_row = 12.5 / 8 / 12 / 15.3 / 10.2 / 14 cycles for s16 affine /
+// s16 linear / s32 / re-based affine / re-based linear / byte-compare s32; with two warps per scheduler
+// (config 2: fewest-instructions row loop) 14 / 10 / 12.5 / 15 / 11 / 14.5, times 1.5 per warp.  A band starts
+// `lag` steps after the band above it (lane skew + 64 steps of poll look-ahead + ~60 steps of L2 visibility);
+// the pair is done when the last band is.  The estimate only steers the choice of kernel, never the result.
 double estimate(long long LQ, long long LT, int mode, int R, int config, int sms, bool two_sided = false) {
   const int rpb = swb::rows_per_band(R, mode);
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
   const int skew = (mode == 2 || mode == 5) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const double per_row = mode == 0 ? 14.0 : (mode == 1 ? 10.0 : (mode == 2 ? 12.5 : (mode == 3 ? 15.0 : (mode == 4 ? 11.0 : 14.5))));
+  static const double kPerRowShort[6] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0};
+  static const double kPerRowLong[6] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5};
+  const double per_row = (config == 2 ? kPerRowLong : kPerRowShort)[mode];
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency

@@ -35,7 +35,9 @@ SWB_HD uint32_t add16x2(uint32_t a, uint32_t b) {
 #endif
 }
 SWB_HD uint32_t addmax16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
+SWB_HD uint32_t addmaxrelu16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }   // max(a+b, c, 0)
 SWB_HD uint32_t max3relu16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2_relu(a, b, c); }
+SWB_HD uint32_t maxrelu16x2(uint32_t a, uint32_t b) { return __vimax_s16x2_relu(a, b); }                         // max(a, b, 0)
 SWB_HD uint32_t max16x2(uint32_t a, uint32_t b) {
 #if SWB_DEVICE_CODE
   return __vmaxs2(a, b);
@@ -54,7 +56,9 @@ SWB_HD uint32_t min16x2(uint32_t a, uint32_t b) {
 }
 SWB_HD uint32_t max3_16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 SWB_HD int addmax32(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
+SWB_HD int addmaxrelu32(int a, int b, int c) { return __viaddmax_s32_relu(a, b, c); }
 SWB_HD int max3relu32(int a, int b, int c) { return __vimax3_s32_relu(a, b, c); }
+SWB_HD int max3_32(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 SWB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #if SWB_DEVICE_CODE

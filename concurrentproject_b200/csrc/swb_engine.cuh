@@ -158,7 +158,7 @@ SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned lo
 SWB_HD int hi_half_max(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a > b ? a : b; }
 SWB_HD int lo_half_min(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a < b ? a : b; }
 
-template <int R, int MODE, int SLACK, bool RB = false>
+template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 2 + SLACK;        // T positions between neighbouring lanes
   constexpr int SKEW = 31 * SK + 1;    // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
@@ -166,6 +166,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   const bool last_lane = lane == 31;
   const int src_lane = (lane + 31) & 31;
   const uint32_t nopen = pack2(-P.gap_init), next = pack2(-P.gap_ext);
+  const uint32_t fnext = pack2(-(P.gap_ext < P.gap_init ? P.gap_ext : P.gap_init));   // F carried down inside a lane
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
   const uint32_t padw = padb * 0x01010101u;
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
@@ -361,25 +362,60 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
           upHo = prmt(yuse, Ho[R - 1], 0x5432u);   // linear mode ships the whole H-open word
           F = 0;
         }
-        uint32_t diag = up_prev, Hup = upHo;
+        uint32_t diag = up_prev;
         up_prev = upHo;
+        if (SHORT) {
+          // Row loop with ONE dependent instruction per row (used with one warp per scheduler, where the
+          // dependency chain and not the issue rate limits a step).  With m = max(diag + s, E, 0):
+          //   F[r]  = max(F[r-1] - min(ext, open), m[r-1] - open)   because H[r-1] = max(m[r-1], F[r-1]);
+          //   Ho[r] = H[r] - open = max(m[r], F[r]) - open.
+          // Only F (affine) or H (linear) is carried from row to row; everything else depends on the previous
+          // column alone.  Row 0 takes the true neighbour values (upHo, F) and the plain recurrence.
+          uint32_t X = upHo, hprev = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t s = prmt(Tlo, Thi, sel[r]);
-          const uint32_t d = add16x2(diag, s);
-          const uint32_t old = Ho[r];
-          uint32_t h;
-          if (MODE == 0) {
-            E[r] = addmax16x2(E[r], next, old);
-            F = addmax16x2(F, next, Hup);
-            h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
-          } else {
-            h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max3relu16x2(d, old, Hup);
+          for (int r = 0; r < R; ++r) {
+            const uint32_t s = prmt(Tlo, Thi, sel[r]);
+            const uint32_t old = Ho[r];
+            uint32_t h;
+            if (MODE == 0) {
+              E[r] = addmax16x2(E[r], next, old);
+              const uint32_t m = RB ? max16x2(addmax16x2(diag, s, E[r]), floorw) : addmaxrelu16x2(diag, s, E[r]);
+              F = addmax16x2(F, r == 0 ? next : fnext, X);
+              X = add16x2(m, nopen);
+              h = max16x2(m, F);
+            } else if (RB) {
+              const uint32_t t = max3_16x2(add16x2(diag, s), old, floorw);
+              h = r == 0 ? max16x2(t, X) : addmax16x2(hprev, nopen, t);
+            } else {
+              const uint32_t t = addmax16x2(diag, s, old);
+              h = r == 0 ? maxrelu16x2(t, X) : addmaxrelu16x2(hprev, nopen, t);
+            }
+            hprev = h;
+            Ho[r] = add16x2(h, nopen);
+            diag = old;
+            if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
           }
-          Ho[r] = add16x2(h, nopen);
-          Hup = Ho[r];
-          diag = old;
-          if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+        } else {
+          // Fewest instructions per row (used with two warps per scheduler, where the issue rate is the limit).
+          uint32_t Hup = upHo;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t s = prmt(Tlo, Thi, sel[r]);
+            const uint32_t d = add16x2(diag, s);
+            const uint32_t old = Ho[r];
+            uint32_t h;
+            if (MODE == 0) {
+              E[r] = addmax16x2(E[r], next, old);
+              F = addmax16x2(F, next, Hup);
+              h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
+            } else {
+              h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max3relu16x2(d, old, Hup);
+            }
+            Ho[r] = add16x2(h, nopen);
+            Hup = Ho[r];
+            diag = old;
+            if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+          }
         }
         Fbot = F;
         xsend = (MODE == 0) ? prmt(Ho[R - 1], Fbot, 0x7632u) : Ho[R - 1];
@@ -417,7 +453,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 // =================================================================================================
 //  GEN: any byte alphabet (the reference compares raw bytes, main.cpp:28-33): the table ring holds the raw T byte
 //  and the substitution score is a compare + select instead of a PRMT table look-up.
-template <int R, int SLACK, bool GEN = false>
+template <int R, int SLACK, bool GEN = false, bool SHORT = true>
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
@@ -425,6 +461,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
   const bool last_lane = lane == 31;
   const int src_lane = (lane + 31) & 31;
   const int nopen = -P.gap_init, next = -P.gap_ext;
+  const int fnext = -(P.gap_ext < P.gap_init ? P.gap_ext : P.gap_init);   // F carried down inside a lane
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
   const uint32_t padw = GEN ? 0x200u : padb * 0x01010101u;       // GEN: 0x200 equals no byte and no pad row (0x100)
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
@@ -563,20 +600,38 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
         const int upHo = SLACK ? yoldH : ynewH;
         int F = SLACK ? yoldF : ynewF;
         yoldH = ynewH; yoldF = ynewF;
-        int diag = up_prev, Hup = upHo;
+        int diag = up_prev;
         up_prev = upHo;
+        if (SHORT) {     // one dependent instruction per row (F only), as in engine_warp_s16
+          int X = upHo;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
-          const int d = diag + s;
-          const int old = Ho[r];
-          E[r] = addmax32(E[r], next, old);
-          F = addmax32(F, next, Hup);
-          const int h = max3relu32(d, E[r], F);
-          Ho[r] = h + nopen;
-          Hup = Ho[r];
-          diag = old;
-          if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
+          for (int r = 0; r < R; ++r) {
+            const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
+            const int old = Ho[r];
+            E[r] = addmax32(E[r], next, old);
+            const int m = addmaxrelu32(diag, s, E[r]);
+            F = addmax32(F, r == 0 ? next : fnext, X);
+            X = m + nopen;
+            const int h = m > F ? m : F;
+            Ho[r] = h + nopen;
+            diag = old;
+            if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
+          }
+        } else {
+          int Hup = upHo;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
+            const int d = diag + s;
+            const int old = Ho[r];
+            E[r] = addmax32(E[r], next, old);
+            F = addmax32(F, next, Hup);
+            const int h = max3relu32(d, E[r], F);
+            Ho[r] = h + nopen;
+            Hup = Ho[r];
+            diag = old;
+            if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
+          }
         }
         xsH = Ho[R - 1];
         xsF = F;

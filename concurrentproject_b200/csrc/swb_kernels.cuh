@@ -12,8 +12,8 @@ constexpr int kNumConfigs = 3;
 SWB_HD int config_wpc(int config) { return config == 2 ? 8 : 4; }
 SWB_HD int config_slack(int config) { return config == 1 ? 1 : 0; }
 
-constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 12, 16};
-constexpr int kNumRowChoices = 8;
+constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16};
+constexpr int kNumRowChoices = 10;
 
 // mode 0: s16x2 affine, 1: s16x2 linear (gap_init == gap_ext), 2: s32 affine,
 // mode 3 / 4: modes 0 / 1 with re-based lanes (scores beyond the s16 range at the packed rate)
@@ -41,10 +41,15 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   const bool second = L.split > 0 && lw_all >= L.split;
   const EngineParams& P = second ? L.b : L.a;
   const int lw = second ? lw_all - L.split : lw_all;
-  if constexpr (MODE == 2) engine_warp_s32<R, SLACK>(P, w, lw, &sm[wi]);
-  else if constexpr (MODE == 5) engine_warp_s32<R, SLACK, true>(P, w, lw, &sm[wi]);
-  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true>(P, w, lw, &sm[wi]);
-  else engine_warp_s16<R, MODE, SLACK>(P, w, lw, &sm[wi]);
+#ifdef SWB_FORCE_LONG_CHAIN                       // measurement builds only (bench/sweep.py A/B)
+  constexpr bool SHORT = false;
+#else
+  constexpr bool SHORT = WPC == 4;     // one warp per scheduler: shortest dependency chain; two: fewest instructions
+#endif
+  if constexpr (MODE == 2) engine_warp_s32<R, SLACK, false, SHORT>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 5) engine_warp_s32<R, SLACK, true, SHORT>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT>(P, w, lw, &sm[wi]);
+  else engine_warp_s16<R, MODE, SLACK, false, SHORT>(P, w, lw, &sm[wi]);
 }
 
 template <int MODE>
@@ -55,7 +60,7 @@ static const void* engine_kernel_lookup(int R, int config) {
          : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \
                        : (const void*)sw_engine_kernel<RR, MODE, 0, 4>;
   switch (R) {
-    SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(12) SWB_CASE(16)
+    SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(10) SWB_CASE(12) SWB_CASE(14) SWB_CASE(16)
     default: return nullptr;
   }
 #undef SWB_CASE

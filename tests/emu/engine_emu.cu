@@ -30,12 +30,21 @@ static std::vector<uint8_t> read_file(const char* path) {
   return v;
 }
 
+// SLACK 1 = launch config 1, SLACK 0 = launch config 2 (the product pairs SLACK 0 / 8 warps per CTA with the
+// long-chain row loop); EMU_SHORT=0/1 overrides the row-loop flavour.
+static int g_short = -1;
 template <int R, int MODE, int SLACK>
 static void run_lane(const EngineParams* P, WarpShared* ws, int lane, int lw, WarpSmem* sm) {
   WarpCtx w{lane, ws};
-  if (MODE == 2) engine_warp_s32<R, SLACK>(*P, w, lw, sm);
-  else if (MODE >= 3) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true>(*P, w, lw, sm);
-  else engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK>(*P, w, lw, sm);
+  const bool sh = g_short < 0 ? SLACK == 1 : g_short != 0;
+  if (MODE == 2) { if (sh) engine_warp_s32<R, SLACK, false, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false>(*P, w, lw, sm); }
+  else if (MODE >= 3) {
+    if (sh) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true>(*P, w, lw, sm);
+    else engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, false>(*P, w, lw, sm);
+  } else {
+    if (sh) engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK, false, true>(*P, w, lw, sm);
+    else engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK, false, false>(*P, w, lw, sm);
+  }
 }
 
 typedef void (*lane_fn)(const EngineParams*, WarpShared*, int, int, WarpSmem*);
@@ -68,6 +77,7 @@ int main(int argc, char** argv) {
   int ma = argc > 9 ? atoi(argv[9]) : 1, mi = argc > 10 ? atoi(argv[10]) : -1, gi = argc > 11 ? atoi(argv[11]) : 1,
       ge = argc > 12 ? atoi(argv[12]) : 1;
   long long link_len = argc > 13 ? atoll(argv[13]) : 4096;
+  if (getenv("EMU_SHORT")) g_short = atoi(getenv("EMU_SHORT"));
   lane_fn fn = pick(R, mode, slack);
   if (!fn) { fprintf(stderr, "unsupported R\n"); return 2; }
 

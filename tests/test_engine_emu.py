@@ -27,12 +27,15 @@ def emu():
         subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(EMU),
                         str(src), "-lpthread"], check=True, cwd=EMU_DIR)
 
-    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp"), final_row=False):
+    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp"), final_row=False, short=None):
         qf, tf, ff = tmp / "swb_emu_q.bin", tmp / "swb_emu_t.bin", tmp / "swb_emu_final.bin"
         qf.write_bytes(bytes(q)); tf.write_bytes(bytes(t))
         ma, mi, gi, ge = p
         env = dict(os.environ, EMU_FINAL=str(ff)) if final_row else dict(os.environ)
         env.pop("EMU_FINAL", None) if not final_row else None
+        env.pop("EMU_SHORT", None)
+        if short is not None:                       # row-loop flavour; default: short chain iff slack == 1
+            env["EMU_SHORT"] = str(int(short))
         out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],
                              capture_output=True, text=True, timeout=900, check=True, env=env).stdout
         d = dict(kv.split("=") for kv in out.split())
@@ -66,6 +69,21 @@ def test_linear_engine_small(emu, slack):
     for k, (n, R, W, G, p) in enumerate([(300, 1, 2, 1, O.DEFAULT), (800, 2, 3, 2, (3, -2, 2, 2)), (1000, 8, 1, 1, (1, -3, 1, 1))]):
         a, b = planted(200 + k, n)
         assert emu(a, b, R, 1, slack, W, G, p) == (O.gotoh_rolling(a, b, p), 0)
+
+
+@pytest.mark.parametrize("short", [0, 1])
+def test_row_loop_flavours_and_gap_open_cheaper_than_extension(emu, short):
+    """Both row-loop flavours (swb_engine.cuh: SHORT = one dependent instruction per row, used by launch configs
+    1 and 3; long = fewest instructions, config 2) under both slacks, including gap_init < gap_ext, where the short
+    flavour carries F down a lane with -min(gap_ext, gap_init)."""
+    a, b = planted(500, 300, 0.08, 0.05)
+    for p in [(2, -1, 1, 3), (3, -2, 0, 0), (2, -3, 5, 1)]:
+        want = O.gotoh_rolling(a, b, p)
+        for mode, slack in ((0, 0), (0, 1), (2, 1 - short), (3, short)):
+            assert emu(a, b, 2, mode, slack, 2, 1, p, short=short) == (want, 0), (p, mode, slack)
+        if p[2] == p[3]:
+            for mode in (1, 4):
+                assert emu(b, a, 1, mode, short, 2, 1, p, short=short) == (want, 0), (p, mode)
 
 
 def test_edge_shapes(emu):

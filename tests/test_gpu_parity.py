@@ -69,16 +69,17 @@ def test_reference_fixture_scores_other_params(api):
         assert api.score(a, b, p, lanes=32) == c["score_main"], c
 
 
-@pytest.mark.parametrize("config", [1, 2])
+@pytest.mark.parametrize("config", [1, 2, 3])
 @pytest.mark.parametrize("lanes,no_linear", [(16, False), (16, True), (32, True)])
 def test_every_kernel_variant_against_oracle(api, config, lanes, no_linear):
     a, b = planted(500, 3000)
     c, d = rng.random_acgt(501, 0, 2100), rng.random_acgt(501, 1, 5000)
-    for p in (O.DEFAULT, (2, -3, 5, 1), (3, -2, 2, 2), (3, -2, 3, 1)):     # the last two: positive drift, every cell matters
+    # (3,-2,2,2), (3,-2,3,1): positive drift, every cell matters; (2,-1,1,3): opening a gap is cheaper than extending it
+    for p in (O.DEFAULT, (2, -3, 5, 1), (3, -2, 2, 2), (3, -2, 3, 1), (2, -1, 1, 3)):
         if p[2] != p[3] and not no_linear:
             continue
         w1, w2 = O.gotoh_rolling(a, b, p), O.gotoh_rolling(c, d, p)
-        for rows in (1, 2, 3, 4, 6, 8, 12, 16):
+        for rows in (1, 2, 3, 4, 6, 8, 10, 12, 14, 16):
             assert api.score(a, b, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w1, (rows, p)
             assert api.score(c, d, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w2, (rows, p)
             assert api.score(d, c, p, lanes=lanes, rows=rows, config=config, no_linear=no_linear) == w2, (rows, p)
@@ -271,7 +272,7 @@ def test_rebased_16_bit_lanes(api, config):
     b = np.concatenate([b[:70000], b[70003:]])               # and one 3-base gap later on
     want = O.gotoh_mt(a, b)
     assert want > 32767
-    for rows, no_linear in ((4, False), (8, True), (16, False), (2, True)):
+    for rows, no_linear in ((4, False), (8, True), (16, False), (2, True), (14, False), (10, True)):
         assert api.score(a, b, lanes=16, rebase=1, rows=rows, config=config, no_linear=no_linear) == want, (rows, no_linear)
         info = api.last_run()
         assert info["rebased"] == 1 and info["engine_launches"] == 1
