@@ -23,7 +23,9 @@ enum Op {
   OP_LOP3, OP_IMAD, OP_IADD32, OP_VIMNMX3_S32_RELU, OP_VIADDMNMX_S32, OP_HFMA2, OP_HMNMX2,
   OP_MIX_VIMNMX3_IMAD, OP_MIX_VIMNMX3_VIADD16, OP_MIX_VIMNMX3_PRMT, OP_MIX_VIADDMNMX_VIADD16,
   OP_MIX_VIMNMX3_HFMA2, OP_MIX_VIADD16_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_VIADDMNMX_IMAD,
-  OP_SHFL, OP_LDS, OP_CELL_AFFINE, OP_CELL_LINEAR, OP_CELL_AFFINE_S32, OP_COUNT
+  OP_SHFL, OP_LDS, OP_CELL_AFFINE, OP_CELL_LINEAR, OP_CELL_AFFINE_S32,
+  OP_VIMNMX_S16X2_RELU, OP_VIADDMNMX_S16X2_RELU, OP_MIX_VIMNMX_VIMNMX3, OP_MIX_VIMNMX_VIADD16, OP_MIX_VIMNMX_PRMT,
+  OP_MIX_ROW_LINEAR, OP_MIX_A3_B1, OP_MIX_A2_MNMX2, OP_COUNT
 };
 
 static const char* op_name[OP_COUNT] = {
@@ -31,7 +33,9 @@ static const char* op_name[OP_COUNT] = {
   "LOP3", "IMAD", "IADD32", "VIMNMX3.S32.RELU", "VIADDMNMX.S32", "HFMA2", "HMNMX2",
   "mix VIMNMX3+IMAD", "mix VIMNMX3+VIADD16", "mix VIMNMX3+PRMT", "mix VIADDMNMX+VIADD16",
   "mix VIMNMX3+HFMA2", "mix VIADD16+IMAD", "mix PRMT+IMAD", "mix VIADDMNMX+IMAD",
-  "SHFL", "LDS", "cell affine s16x2 (6.5 instr)", "cell linear s16x2 (4.5 instr)", "cell affine s32 (6.5 instr)"
+  "SHFL", "LDS", "cell affine s16x2 (6.5 instr)", "cell linear s16x2 (4.5 instr)", "cell affine s32 (6.5 instr)",
+  "VIMNMX.S16x2.RELU", "VIADDMNMX.S16x2.RELU", "mix VIMNMX+VIMNMX3", "mix VIMNMX+VIADD16", "mix VIMNMX+PRMT",
+  "mix PRMT+VIADDMNMX.RELU+VIMNMX+VIADD16 (linear row)", "mix PRMT+VIADDMNMX+VIMNMX3+VIADD16", "mix PRMT+VIADDMNMX+2xVIMNMX"
 };
 
 __device__ __forceinline__ uint32_t hfma2_u(uint32_t x, uint32_t a, uint32_t b) {
@@ -73,6 +77,17 @@ __device__ __forceinline__ uint32_t apply(uint32_t x, uint32_t a, uint32_t b, in
   else if constexpr (OP == OP_MIX_VIADD16_IMAD) return (k & 1) ? imad_u(x, a, b) : __vadd2(x, a);
   else if constexpr (OP == OP_MIX_PRMT_IMAD) return (k & 1) ? imad_u(x, a, b) : __byte_perm(x, a, b);
   else if constexpr (OP == OP_MIX_VIADDMNMX_IMAD) return (k & 1) ? imad_u(x, a, b) : __viaddmax_s16x2(x, a, b);
+  else if constexpr (OP == OP_VIMNMX_S16X2_RELU) return __vimax_s16x2_relu(x, a);
+  else if constexpr (OP == OP_VIADDMNMX_S16X2_RELU) return __viaddmax_s16x2_relu(x, a, b);
+  else if constexpr (OP == OP_MIX_VIMNMX_VIMNMX3) return (k & 1) ? __vmaxs2(x, a) : __vimax3_s16x2_relu(x, a, b);
+  else if constexpr (OP == OP_MIX_VIMNMX_VIADD16) return (k & 1) ? __vmaxs2(x, a) : __vadd2(x, a);
+  else if constexpr (OP == OP_MIX_VIMNMX_PRMT) return (k & 1) ? __vmaxs2(x, a) : __byte_perm(x, a, b);
+  else if constexpr (OP == OP_MIX_ROW_LINEAR)
+    return (k & 3) == 0 ? __byte_perm(x, a, b) : ((k & 3) == 1 ? __viaddmax_s16x2_relu(x, a, b) : ((k & 3) == 2 ? __vmaxs2(x, a) : __vadd2(x, a)));
+  else if constexpr (OP == OP_MIX_A3_B1)
+    return (k & 3) == 0 ? __byte_perm(x, a, b) : ((k & 3) == 1 ? __viaddmax_s16x2(x, a, b) : ((k & 3) == 2 ? __vimax3_s16x2_relu(x, a, b) : __vadd2(x, a)));
+  else if constexpr (OP == OP_MIX_A2_MNMX2)
+    return (k & 3) == 0 ? __byte_perm(x, a, b) : ((k & 3) == 1 ? __viaddmax_s16x2(x, a, b) : __vmaxs2(x, a));
   else if constexpr (OP == OP_SHFL) return __shfl_sync(0xffffffffu, x, (int)(a & 31));
   else if constexpr (OP == OP_LDS) return sm[(x + a) & 1023];
   else return x;
@@ -248,6 +263,8 @@ int main(int argc, char** argv) {
   CH8(OP_MIX_VIMNMX3_IMAD) CH8(OP_MIX_VIMNMX3_VIADD16) CH8(OP_MIX_VIMNMX3_PRMT) CH8(OP_MIX_VIADDMNMX_VIADD16)
   CH8(OP_MIX_VIMNMX3_HFMA2) CH8(OP_MIX_VIADD16_IMAD) CH8(OP_MIX_PRMT_IMAD) CH8(OP_MIX_VIADDMNMX_IMAD)
   CH8(OP_SHFL) CH8(OP_LDS)
+  CH8(OP_VIMNMX_S16X2_RELU) CH8(OP_VIADDMNMX_S16X2_RELU) CH8(OP_MIX_VIMNMX_VIMNMX3) CH8(OP_MIX_VIMNMX_VIADD16)
+  CH8(OP_MIX_VIMNMX_PRMT) CH8(OP_MIX_ROW_LINEAR) CH8(OP_MIX_A3_B1) CH8(OP_MIX_A2_MNMX2)
   bench_cell<0, 2>(f, IT); bench_cell<0, 4>(f, IT); bench_cell<0, 8>(f, IT); bench_cell<0, 16>(f, IT);
   bench_cell<1, 4>(f, IT); bench_cell<1, 8>(f, IT); bench_cell<1, 16>(f, IT);
   bench_cell<2, 4>(f, IT); bench_cell<2, 8>(f, IT);

@@ -130,8 +130,7 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
             const uint32_t xs = (u == 15) ? nopen : HoB;
             const uint32_t rv = w.shfl(xs, src_prev);
             leftHo = prmt(rv, HoB, 0x5432u);
-            const uint32_t d = add16x2(HoA, sA);
-            h2 = max3relu16x2(d, leftHo, HoB);
+            h2 = max16x2(addmaxrelu16x2(HoA, sA, leftHo), HoB);
           }
           HoA = add16x2(h2, nopen);
           best = max16x2(best, h2);
@@ -153,8 +152,7 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
             const uint32_t xs = (u == 0) ? nopen : HoA;
             const uint32_t rv = w.shfl(xs, src_next);
             upHo = prmt(HoA, rv, 0x5432u);
-            const uint32_t d = add16x2(HoB, sB);
-            h2 = max3relu16x2(d, HoA, upHo);
+            h2 = max16x2(addmaxrelu16x2(HoB, sB, HoA), upHo);
           }
           HoB = add16x2(h2, nopen);
           best = max16x2(best, h2);

@@ -121,15 +121,16 @@ SWB_HD void batch_warp(const BatchParams& P, const WarpCtx& w, long long warp_id
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const uint32_t s = prmt(Tlo, Thi, sel[r]);
-          const uint32_t d = add16x2(diag, s);
           const uint32_t old = Ho[r];
           uint32_t h;
           if (MODE == 0) {
+            const uint32_t d = add16x2(diag, s);
             E[r] = addmax16x2(E[r], next, old);
             F = addmax16x2(F, next, Hup);
             h = max3relu16x2(d, E[r], F);
           } else {
-            h = max3relu16x2(d, old, Hup);
+            // the clamp at 0 rides on the fused add-max; the second max is then the plain (full-rate) VIMNMX
+            h = max16x2(addmaxrelu16x2(diag, s, old), Hup);
           }
           Ho[r] = add16x2(h, nopen);
           Hup = Ho[r];

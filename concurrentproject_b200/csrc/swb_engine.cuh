@@ -409,7 +409,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
               F = addmax16x2(F, next, Hup);
               h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
             } else {
-              h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max3relu16x2(d, old, Hup);
+              // non-RB: the clamp at 0 rides on the fused add-max, the second max is the plain full-rate VIMNMX
+              h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max16x2(addmaxrelu16x2(diag, s, old), Hup);
             }
             Ho[r] = add16x2(h, nopen);
             Hup = Ho[r];
