@@ -85,6 +85,19 @@ def score(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS, *, l
     return out.value
 
 
+def score_end(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS) -> Tuple[int, int, int]:
+    """(score, i_end, j_end): the score and the 1-based end cell of the best local alignment -- i_end in seq2,
+    j_end in seq1; among cells holding the maximum the one with the smallest j_end, then the smallest i_end; (0, 0)
+    for score 0 (swb200_score_end).  New relative to the score-only reference (README.md:6)."""
+    a, b = _u8(seq1), _u8(seq2)
+    out, ie, je = C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+    p = _params(params)
+    rc = _lib.load().swb200_score_end(_ptr(a), len(a), _ptr(b), len(b), C.byref(p), C.byref(out), C.byref(ie), C.byref(je))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_end")
+    return out.value, ie.value, je.value
+
+
 def last_run(ctx: Optional["Context"] = None) -> dict:
     info = RunInfo()
     rc = _lib.load().swb200_last_run(ctx.handle if ctx else None, C.byref(info))
@@ -125,6 +138,17 @@ class Context:
         if rc != 0:
             raise SwbError(rc, "swb200_score_device")
         return out.value
+
+    def score_end_device(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *,
+                         stream: int = 0) -> Tuple[int, int, int]:
+        """score_end for sequences resident in HBM (swb200_score_end_device)."""
+        out, ie, je = C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        p = _params(params)
+        rc = _lib.load().swb200_score_end_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
+                                                 C.c_void_p(stream), C.byref(out), C.byref(ie), C.byref(je))
+        if rc != 0:
+            raise SwbError(rc, "swb200_score_end_device")
+        return out.value, ie.value, je.value
 
     def last_run(self) -> dict:
         return last_run(self)

@@ -184,6 +184,7 @@ struct swb200_ctx {
   uint2* d_links = nullptr; size_t links_cap = 0;  // entries
   uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
   unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
+  int* d_cand = nullptr; size_t cand_cap = 0;     // end-cell tracking: {H, T position, Q row} per band
   int* d_result = nullptr;        // [0] score [1] status, [2..9] presence bitmap
   uint8_t* d_lut = nullptr;       // 256 bytes
   int* h_result = nullptr;        // pinned
@@ -264,8 +265,30 @@ bool rebase_is_safe(const swb200_params& p, int R) {
   return step * (64LL * R + 96 + swb::kRebaseBlock + 64) <= 10000;
 }
 
+// End-cell tracking: reduce the per-band candidates {H, T position, Q row} to the best H, then the smallest
+// T position, then the smallest Q row (the rule every warp already applied inside its band).  One block.
+__global__ void reduce_end_kernel(const int* cand, int nb, int* out3) {
+  __shared__ int sh[256], sp[256], sr[256];
+  int h = 0, p = 0x7fffffff, r = 0x7fffffff;
+  for (int b = (int)threadIdx.x; b < nb; b += 256) {
+    const int ch = cand[3 * b], cp = cand[3 * b + 1], cr = cand[3 * b + 2];
+    if (ch > h || (ch == h && (cp < p || (cp == p && cr < r)))) { h = ch; p = cp; r = cr; }
+  }
+  sh[threadIdx.x] = h; sp[threadIdx.x] = p; sr[threadIdx.x] = r;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      const int oh = sh[threadIdx.x + d], op = sp[threadIdx.x + d], orr = sr[threadIdx.x + d];
+      const int mh = sh[threadIdx.x], mp = sp[threadIdx.x], mr = sr[threadIdx.x];
+      if (oh > mh || (oh == mh && (op < mp || (op == mp && orr < mr)))) { sh[threadIdx.x] = oh; sp[threadIdx.x] = op; sr[threadIdx.x] = orr; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out3[0] = sh[0]; out3[1] = sp[0]; out3[2] = sr[0]; }
+}
+
 struct Plan {
-  int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine, 3/4 = 0/1 with re-based lanes
+  int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine, 3/4 = 0/1 with re-based lanes, 5 s32 bytes, 6/7 = 2/5 + end cell
   int R, config, ctas;
   bool swap;     // Q = seq2 instead of seq1
   bool two_sided;  // forward sweep over the top half of the rows + reversed sweep over the bottom half
@@ -283,9 +306,9 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
-  const int skew = (mode == 2 || mode == 5) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  static const double kPerRowShort[6] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0};
-  static const double kPerRowLong[6] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5};
+  const int skew = swb::mode_is_s32(mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  static const double kPerRowShort[8] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0, 14.0, 16.0};
+  static const double kPerRowLong[8] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5, 14.5, 16.5};
   const double per_row = (config == 2 ? kPerRowLong : kPerRowShort)[mode];
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
@@ -311,6 +334,8 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   pl.mode = lanes == 32 ? 2 : ((p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0);
   if (lanes == 17) pl.mode += 3;
   if (lanes == 33) pl.mode = 5;          // 32-bit lanes, any byte alphabet
+  if (lanes == 34) pl.mode = 6;          // 32-bit lanes + position of the maximum
+  if (lanes == 35) pl.mode = 7;          // the same for any byte alphabet
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
@@ -338,6 +363,8 @@ const void* kernel_for(const Plan& pl) {
     case 2: return swb::engine_kernel_mode2(pl.R, pl.config);
     case 3: return swb::engine_kernel_mode3(pl.R, pl.config);
     case 4: return swb::engine_kernel_mode4(pl.R, pl.config);
+    case 6: return swb::engine_kernel_mode6(pl.R, pl.config);
+    case 7: return swb::engine_kernel_mode7(pl.R, pl.config);
     default: return swb::engine_kernel_mode5(pl.R, pl.config);
   }
 }
@@ -356,7 +383,7 @@ struct RingCfg {
 // Encode + one engine run at a fixed lane width.  d_seq1/d_seq2 are device pointers.
 int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
              const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
-             int* score, int* status, const RingCfg* ring = nullptr) {
+             int* score, int* status, const RingCfg* ring = nullptr, int* end3 = nullptr) {
   const int world = ring ? ring->world : 1;
   const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr);
   const void* kern = kernel_for(pl);
@@ -389,7 +416,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int warps = (int)ctas * wpc;
   const int split = ts ? warps / 2 : 0;
 
-  const int skew = (pl.mode == 2 || pl.mode == 5) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const int skew = swb::mode_is_s32(pl.mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
   const int align = (pl.mode == 3 || pl.mode == 4) ? swb::kRebaseBlock : swb::kChunk;
   const long long nsteps = ((LT + skew + align - 1) / align) * align;
   const int ext_shift = std::max(4, log2_ceil(nsteps + swb::kChunk));
@@ -414,6 +441,9 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
   } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
   if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 4, false, s))) return rc;
+  const bool track = pl.mode == 6 || pl.mode == 7;
+  if (track && (ring || !end3)) return fail(SWB200_ERR_ARG, "end-cell tracking runs on one GPU through swb200_score_end");
+  if (track && (rc = grow(c->d_cand, c->cand_cap, 3 * (size_t)NB + 3, false, s))) return rc;
 
   // tags carry a 6-bit epoch; when it wraps, forget every old tag
   c->epoch += 1;
@@ -425,7 +455,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
-  const bool generic = pl.mode == 5;       // raw bytes straight from the caller's buffers, nothing to encode
+  const bool generic = pl.mode == 5 || pl.mode == 7;       // raw bytes straight from the caller's buffers, nothing to encode
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
   const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
   if (!generic) {
@@ -462,6 +492,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     SWB_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)warps * 4 * sizeof(long long), s));
   }
   P.prof = d_prof;
+  P.cand = track ? c->d_cand : nullptr;
   L.split = split;
   if (ts) {
     P.final_out = c->d_final; P.final_mask = (unsigned)(ext_len - 1);
@@ -483,9 +514,15 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
                                                         p.gap_init, p.gap_ext, c->d_result);
     c->info.aux_launches += 1;
   }
+  if (track) {
+    reduce_end_kernel<<<1, 256, 0, s>>>(c->d_cand, (int)NB, c->d_result + 24);
+    c->info.aux_launches += 1;
+  }
   SWB_CUDA(cudaEventRecord(c->ev1, s));
   SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 10 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (track) SWB_CUDA(cudaMemcpyAsync(c->h_result + 24, c->d_result + 24, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
   SWB_CUDA(cudaStreamSynchronize(s));
+  if (track) { end3[0] = c->h_result[24]; end3[1] = c->h_result[25]; end3[2] = c->h_result[26]; }
   float ms = 0;
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   *score = c->h_result[0];
@@ -512,7 +549,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u ts=%d]\n",
             c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
             c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch, (int)ts);
-  c->info.lanes = (pl.mode == 2 || pl.mode == 5) ? 32 : 16; c->info.rebased = pl.mode == 3 || pl.mode == 4;
+  c->info.lanes = swb::mode_is_s32(pl.mode) ? 32 : 16; c->info.rebased = pl.mode == 3 || pl.mode == 4;
   c->info.linear = pl.mode == 1 || pl.mode == 4;
   c->info.two_sided = ts;
   c->info.rows = pl.R; c->info.config = pl.config;
@@ -522,17 +559,25 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
 }
 
 // Full policy for one pair whose bytes are in device memory.
+// end_out != nullptr: also report the end cell {i_end (1-based position in seq2), j_end (in seq1)} of the best local
+// alignment -- among cells with the maximal score the one with the smallest j, then the smallest i; {0, 0} for
+// score 0.  Runs the 32-bit tracking kernel with seq2 striped and seq1 streamed, whatever the options say.
 int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
-                        const swb200_params* pp, const swb200_options* oo, cudaStream_t s, int* score_out) {
+                        const swb200_params* pp, const swb200_options* oo, cudaStream_t s, int* score_out,
+                        long long* end_out = nullptr) {
   const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
-  const swb200_options o = oo ? *oo : swb200_options{};
+  swb200_options o = oo ? *oo : swb200_options{};
+  if (end_out) { o.orient = 2; o.lanes = 0; o.two_sided = -1; o.rebase = -1; if (o.rows > 16) o.rows = 16; }
   int rc;
   if ((rc = check_params(p))) return rc;
   if (n < 0 || m < 0 || !score_out) return fail(SWB200_ERR_ARG, "negative length or null output");
   if (o.lanes != 0 && o.lanes != 16 && o.lanes != 32) return fail(SWB200_ERR_ARG, "lanes must be 0, 16 or 32");
   c->info = swb200_run_info{};
   c->info.cells = n * m;
+  if (end_out) { end_out[0] = 0; end_out[1] = 0; }
   if (n == 0 || m == 0) { *score_out = 0; return SWB200_OK; }   // both reference oracles return 0 here
+  if (end_out && ((long long)p.match * std::min(n, m) >= (1LL << 20) || std::max(n, m) >= (1LL << 30)))
+    return fail(SWB200_ERR_RANGE, "end-cell tracking needs match*min(n,m) < 2^20");
   SWB_CUDA(cudaSetDevice(c->device));
 
   const uint8_t* lut = nullptr;
@@ -544,14 +589,16 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
   const bool rb_ok = o.rebase >= 0 && o.lanes != 32 && rebase_is_safe(p, o.rows ? o.rows : 16);
   int lanes = o.lanes == 32 ? 32 : 16;
   if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 8LL * 32767)) lanes = 17;
+  if (end_out) lanes = 34;
+  int end3[3] = {0, 0, 0};
   // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
   // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
   // leaving the range and we repeat in 32 bits (bit-exact either way).
   for (int attempt = 0; attempt < 4; ++attempt) {
     int score = 0, status = 0;
-    if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status))) return rc;
+    if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status, nullptr, end_out ? end3 : nullptr))) return rc;
     if (status & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off timed out");
-    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33) {
+    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33 && lanes != 35) {
       if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
       // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
       SWB_CUDA(cudaMemsetAsync(c->d_result + 16, 0, 8 * sizeof(int), s));
@@ -570,7 +617,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
         }
       if (distinct > 4) {
         // the reference compares raw bytes (main.cpp:28-33): score such pairs with the byte-compare kernel
-        lanes = 33;
+        lanes = end_out ? 35 : 33;
         continue;
       }
       SWB_CUDA(cudaMemcpyAsync(c->d_lut, table, 256, cudaMemcpyHostToDevice, s));
@@ -589,6 +636,11 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
       continue;
     }
     *score_out = score;
+    if (end_out && score > 0) {
+      if (end3[0] != score) return fail(SWB200_ERR_CUDA, "internal: tracked maximum differs from the score");
+      end_out[0] = (long long)end3[2] + 1;      // Q row -> position in seq2
+      end_out[1] = (long long)end3[1] + 1;      // T position -> position in seq1
+    }
     return SWB200_OK;
   }
   return fail(SWB200_ERR_CUDA, "internal: retry budget exhausted");
@@ -668,7 +720,7 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
-  cudaFree(c->d_progress); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);
   cudaFreeHost(c->h_result);
@@ -707,6 +759,43 @@ int swb200_score_ex(const unsigned char* seq1, long long n, const unsigned char*
   SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
   SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
   return score_device_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, opt, s, score_out);
+}
+
+int swb200_score_end_device(swb200_ctx* c, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2,
+                            long long m, const swb200_params* p, void* stream, int* score_out, long long* i_end,
+                            long long* j_end) {
+  if (!c || !i_end || !j_end) return fail(SWB200_ERR_ARG, "null context or output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  long long e[2] = {0, 0};
+  const int rc = score_device_locked(c, d_seq1, n, d_seq2, m, p, nullptr, (cudaStream_t)stream, score_out, e);
+  *i_end = e[0]; *j_end = e[1];
+  return rc;
+}
+
+int swb200_score_end(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                     const swb200_params* p, int* score_out, long long* i_end, long long* j_end) {
+  if (n < 0 || m < 0 || !score_out || !i_end || !j_end || (n > 0 && !seq1) || (m > 0 && !seq2))
+    return fail(SWB200_ERR_ARG, "bad sequence arguments");
+  *i_end = 0; *j_end = 0;
+  if (n == 0 || m == 0) {
+    if (p) { int rc = check_params(*p); if (rc) return rc; }
+    *score_out = 0;
+    return SWB200_OK;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->own_stream;
+  const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
+  if ((rc = grow(c->d_ascii, c->ascii_cap, off2 + (size_t)m + 256, false, s))) return rc;
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
+  long long e[2] = {0, 0};
+  rc = score_device_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, nullptr, s, score_out, e);
+  *i_end = e[0]; *j_end = e[1];
+  return rc;
 }
 
 int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, int m, const swb200_params* p,

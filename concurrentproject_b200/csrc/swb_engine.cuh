@@ -61,6 +61,7 @@ struct EngineParams {
   long long spin_limit;         // polls before a waiting warp gives up (sets STATUS_SPIN_TIMEOUT)
   int dbg;                      // timing experiments only: 1 = no boundary stores, 2 = no boundary polls
   long long* prof;              // optional [warps_local][4]: cycles in prologue, cycles in steps, failed polls, chunks
+  int* cand;                    // TRACK kernels: per band {best H, its T position, its Q row} (first in column-major order)
 };
 
 struct WarpSmem {
@@ -454,7 +455,13 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 // =================================================================================================
 //  GEN: any byte alphabet (the reference compares raw bytes, main.cpp:28-33): the table ring holds the raw T byte
 //  and the substitution score is a compare + select instead of a PRMT table look-up.
-template <int R, int SLACK, bool GEN = false, bool SHORT = true>
+//  TRACK: also report WHERE the maximum is (the reference is score-only).  The running best
+//  becomes a key  H << 11 | (127 - step mod 128) << 4 | (15 - row in lane):  one max keeps the highest H and,
+//  among equals, the earliest step (= smallest T position for a lane) and then the smallest row; which 128-step
+//  window the key belongs to is noted once per chunk, when the lane's best H has grown.  Per band the warp
+//  reduces (max H, min T position, min Q row) into P.cand; the host reduces the bands by the same rule.
+//  Needs H < 2^20 and R <= 16.
+template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = false>
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
@@ -507,6 +514,8 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
     int up_prev = nopen, xsH = nopen, xsF = nopen, yoldH = nopen, yoldF = nopen;
+    int bestkey = 0, rec_h = 0, rec_key = 0;         // TRACK only
+    long long rec_win = 0;
 
     w.sync();
 #pragma unroll
@@ -589,6 +598,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 
       uint32_t Tnext = tabp[0];
       int xnH = (int)inbp[0], xnF = (int)inbp[2 * kInbox];
+      int cstep = ((127 - (int)(i0 & 127)) << 4) + 15;      // TRACK: low key bits of row 0 at the chunk's first step
 #pragma unroll 4
       for (int k = 0; k < kChunk; ++k) {
         const uint32_t Tw = Tnext;
@@ -616,7 +626,8 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
             const int h = m > F ? m : F;
             Ho[r] = h + nopen;
             diag = old;
-            if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
+            if (TRACK) { const int key = h * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
+            else if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
           }
         } else {
           int Hup = upHo;
@@ -631,9 +642,11 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
             Ho[r] = h + nopen;
             Hup = Ho[r];
             diag = old;
-            if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
+            if (TRACK) { const int key = h * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
+            else if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
           }
         }
+        if (TRACK) cstep -= 16;
         xsH = Ho[R - 1];
         xsF = F;
         if (emit) {
@@ -641,6 +654,25 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
           st_entry(outp + 2 * k + 1, (uint32_t)xsF, otag);
         }
       }
+      if (TRACK) {                                     // once per chunk: has this lane's best H grown?
+        const int hb = bestkey >> 11;
+        const bool upd = hb > rec_h;
+        rec_h = upd ? hb : rec_h;
+        rec_key = upd ? bestkey : rec_key;
+        rec_win = upd ? (i0 & ~127LL) : rec_win;
+      }
+    }
+    if (TRACK) {
+      // this lane's first best cell: step -> T position (lane l is SK*l positions behind lane 0), row in Q
+      const long long step = rec_win + 127 - ((rec_key >> 4) & 127);
+      const int pos = (int)(step - (long long)SK * lane);
+      const int row = (int)(band * (32LL * R) + (long long)lane * R + (15 - (rec_key & 15)));
+      const int hmax = w.reduce_max(rec_h);
+      const int pmin = -w.reduce_max(rec_h == hmax ? -pos : -0x7fffffff);
+      const int rmin = -w.reduce_max((rec_h == hmax && pos == pmin) ? -row : -0x7fffffff);
+      if (lane == 0) { P.cand[3 * band] = hmax; P.cand[3 * band + 1] = pmin; P.cand[3 * band + 2] = rmin; }
+      best0 = best0 > hmax ? best0 : hmax;
+      bestkey = 0; rec_h = 0; rec_key = 0; rec_win = 0;
     }
     if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + nsteps));
   }
@@ -649,6 +681,8 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 }
 
 // rows of Q one band covers
-SWB_HD int rows_per_band(int R, int mode) { return ((mode == 2 || mode == 5) ? 32 : 64) * R; }
+// modes 2, 5, 6, 7 run 32-bit lanes (6, 7 = 2, 5 with end-cell tracking)
+SWB_HD bool mode_is_s32(int mode) { return mode == 2 || mode >= 5; }
+SWB_HD int rows_per_band(int R, int mode) { return (mode_is_s32(mode) ? 32 : 64) * R; }
 
 }  // namespace swb

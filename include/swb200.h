@@ -79,6 +79,17 @@ SWB200_API int swb200_score_device(swb200_ctx* ctx, const unsigned char* d_seq1,
                         const unsigned char* d_seq2, long long m, const swb200_params* p,
                         const swb200_options* opt, void* stream, int* score_out);
 
+/* ---- score AND end cell (the reference is score-only, README.md:6) -----------
+ * i_end / j_end: 1-based positions in seq2 / seq1 of the last aligned pair of the best local alignment,
+ * i.e. the cell (i, j) of main.cpp's H matrix that holds the maximum; among several such cells the one with
+ * the smallest j, then the smallest i.  Score 0 gives (0, 0).  One pass of the 32-bit tracking kernel;
+ * needs match * min(n, m) < 2^20 (SWB200_ERR_RANGE otherwise). */
+SWB200_API int swb200_score_end(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                     const swb200_params* p, int* score_out, long long* i_end, long long* j_end);
+SWB200_API int swb200_score_end_device(swb200_ctx* ctx, const unsigned char* d_seq1, long long n,
+                            const unsigned char* d_seq2, long long m, const swb200_params* p, void* stream,
+                            int* score_out, long long* i_end, long long* j_end);
+
 /* What the last swb200_score*_ call on this context actually ran. */
 typedef struct {
   int lanes;            /* 16 or 32 */

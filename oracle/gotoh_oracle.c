@@ -77,6 +77,38 @@ int oracle_gotoh_rolling(const unsigned char* seq1, const unsigned char* seq2, i
   return best;
 }
 
+/* main.cpp:57-63 with rolling rows, remembering where the maximum sits (rule in the header). */
+int oracle_gotoh_end(const unsigned char* seq1, const unsigned char* seq2, int n, int m, const oracle_params* p,
+                     int* i_end, int* j_end) {
+  *i_end = 0; *j_end = 0;
+  if (n < 0 || m < 0) return -1;
+  int* Hrow = (int*)calloc((size_t)n + 1, sizeof(int));
+  int* Frow = (int*)calloc((size_t)n + 1, sizeof(int));
+  if (!Hrow || !Frow) { free(Hrow); free(Frow); return -1; }
+  const int ge = p->gap_ext, gi = p->gap_init;
+  int best = 0, bi = 0, bj = 0;
+  for (int i = 1; i <= m; ++i) {
+    const unsigned char b = seq2[i - 1];
+    int e = 0, hleft = 0, hdiag = 0;
+    for (int j = 1; j <= n; ++j) {
+      e = imax(e - ge, hleft - gi);
+      const int f = imax(Frow[j] - ge, Hrow[j] - gi);
+      int h = hdiag + (seq1[j - 1] == b ? p->match : p->mismatch);
+      if (e > h) h = e;
+      if (f > h) h = f;
+      if (h < 0) h = 0;
+      hdiag = Hrow[j];
+      Hrow[j] = h;
+      Frow[j] = f;
+      hleft = h;
+      if (h > best || (h == best && h > 0 && (j < bj || (j == bj && i < bi)))) { best = h; bi = i; bj = j; }
+    }
+  }
+  free(Hrow); free(Frow);
+  *i_end = bi; *j_end = bj;
+  return best;
+}
+
 int oracle_gotoh_last_row(const unsigned char* seq1, const unsigned char* seq2, int n, int m,
                           const oracle_params* p, int* Hrow_out, int* Frow_out) {
   if (n < 0 || m < 0) return -1;

@@ -38,6 +38,7 @@ static void run_lane(const EngineParams* P, WarpShared* ws, int lane, int lw, Wa
   WarpCtx w{lane, ws};
   const bool sh = g_short < 0 ? SLACK == 1 : g_short != 0;
   if (MODE == 2) { if (sh) engine_warp_s32<R, SLACK, false, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false>(*P, w, lw, sm); }
+  else if (MODE == 6) { if (sh) engine_warp_s32<R, SLACK, false, true, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false, true>(*P, w, lw, sm); }
   else if (MODE >= 3) {
     if (sh) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true>(*P, w, lw, sm);
     else engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, false>(*P, w, lw, sm);
@@ -55,6 +56,7 @@ static lane_fn pick2(int mode, int slack) {
   if (mode == 1) return slack ? run_lane<R, 1, 1> : run_lane<R, 1, 0>;
   if (mode == 3) return slack ? run_lane<R, 3, 1> : run_lane<R, 3, 0>;
   if (mode == 4) return slack ? run_lane<R, 4, 1> : run_lane<R, 4, 0>;
+  if (mode == 6) return slack ? run_lane<R, 6, 1> : run_lane<R, 6, 0>;      // 32-bit lanes + end cell
   return slack ? run_lane<R, 2, 1> : run_lane<R, 2, 0>;
 }
 static lane_fn pick(int R, int mode, int slack) {
@@ -89,7 +91,7 @@ int main(int argc, char** argv) {
 
   const int rpb = rows_per_band(R, mode);
   const int NB = (int)((LQ + rpb - 1) / rpb);
-  const long long skew = mode == 2 ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const long long skew = (mode == 2 || mode == 6) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
   const int align = mode >= 3 ? kRebaseBlock : kChunk;
   long long nsteps = ((LT + skew + align - 1) / align) * align;
   long long ext_len = 1; int ext_shift = 0;
@@ -97,6 +99,7 @@ int main(int argc, char** argv) {
   int link_shift = 0; while ((1LL << link_shift) < link_len) ++link_shift;
 
   int result[2] = {0, 0};
+  std::vector<int> cand((size_t)3 * (NB + 1), 0);        // mode 6: {H, T position, Q row} per band
   std::vector<std::vector<uint2>> links(G), ext(G);
   std::vector<std::vector<unsigned long long>> progress(G);
   std::vector<EngineParams> P(G);
@@ -116,6 +119,7 @@ int main(int argc, char** argv) {
     p.tag_base = epoch << 26; p.ext_tag_base = (epoch << 26) | 0x5Au; p.result = result;
     p.match = ma; p.mismatch = mi; p.gap_init = gi; p.gap_ext = ge;
     p.spin_limit = 200000000LL;
+    p.cand = cand.data();
   }
   // optional: the last band's bottom boundary row (what the two-sided sweep combines), dumped to $EMU_FINAL
   std::vector<uint2> final_row((size_t)4 * ext_len, make_uint2(0, 0));
@@ -129,7 +133,16 @@ int main(int argc, char** argv) {
       for (int l = 0; l < 32; ++l)
         th.emplace_back(fn, &P[g], &ws[(size_t)g * W + w], l, w, &sm[(size_t)g * W + w]);
   for (auto& x : th) x.join();
-  printf("score=%d status=%d bands=%d nsteps=%lld\n", result[0], result[1], NB, nsteps);
+  printf("score=%d status=%d bands=%d nsteps=%lld", result[0], result[1], NB, nsteps);
+  if (mode == 6) {   // the host's reduction: best H, then smallest T position, then smallest Q row
+    int h = 0, pp = 0x7fffffff, rr = 0x7fffffff;
+    for (int b = 0; b < NB; ++b) {
+      const int ch = cand[3 * b], cp = cand[3 * b + 1], cr = cand[3 * b + 2];
+      if (ch > h || (ch == h && (cp < pp || (cp == pp && cr < rr)))) { h = ch; pp = cp; rr = cr; }
+    }
+    printf(" endh=%d endpos=%d endrow=%d", h, pp, rr);
+  }
+  printf("\n");
   if (getenv("EMU_FINAL")) {
     FILE* f = fopen(getenv("EMU_FINAL"), "wb");
     long long hdr[2] = {LT, skew};

@@ -60,6 +60,8 @@ def oracle():
             getattr(lib, name).restype = C.c_int
         lib.oracle_gotoh_last_row.argtypes = sig + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.oracle_gotoh_last_row.restype = C.c_int
+        lib.oracle_gotoh_end.argtypes = sig + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.oracle_gotoh_end.restype = C.c_int
         lib.oracle_gotoh_mt.argtypes = sig + [C.c_int]
         lib.oracle_gotoh_mt.restype = C.c_int
         lib.oracle_gotoh_banded.argtypes = sig[:4] + [C.c_int, C.c_int, C.POINTER(OracleParams), C.POINTER(C.c_int64)]
@@ -113,6 +115,15 @@ def gotoh_last_row(s1, s2, p=DEFAULT):
     best = oracle().oracle_gotoh_last_row(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), H.ctypes.data_as(C.POINTER(C.c_int)),
                                           F.ctypes.data_as(C.POINTER(C.c_int)))
     return best, H, F
+
+
+def gotoh_end(s1, s2, p=DEFAULT):
+    """(score, i_end, j_end): 1-based end cell of the best local alignment, i in seq2, j in seq1; smallest j, then i."""
+    a, b = _u8(s1), _u8(s2)
+    pp = _params(p)
+    ie, je = C.c_int(0), C.c_int(0)
+    best = oracle().oracle_gotoh_end(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), C.byref(ie), C.byref(je))
+    return best, ie.value, je.value
 
 
 def gotoh_mt(s1, s2, p=DEFAULT, threads=0):

@@ -39,6 +39,8 @@ def emu():
         out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],
                              capture_output=True, text=True, timeout=900, check=True, env=env).stdout
         d = dict(kv.split("=") for kv in out.split())
+        if mode == 6:      # end-cell tracking: (score, status, 1-based row in Q, 1-based position in T)
+            return int(d["score"]), int(d["status"]), int(d["endrow"]) + 1, int(d["endpos"]) + 1, int(d["endh"])
         if not final_row:
             return int(d["score"]), int(d["status"])
         raw = ff.read_bytes()
@@ -88,6 +90,24 @@ def test_row_loop_flavours_and_gap_open_cheaper_than_extension(emu, short):
         if p[2] == p[3]:
             for mode in (1, 4):
                 assert emu(b, a, 1, mode, short, 2, 1, p, short=short) == (want, 0), (p, mode)
+
+
+@pytest.mark.parametrize("slack", [0, 1])
+def test_end_cell_tracking(emu, slack):
+    """32-bit tracking engine: the end cell of the best local alignment -- highest H, then the
+    smallest T position, then the smallest Q row -- across lanes, bands, rounds and 128-step key windows; with zero
+    gap costs (3,-2,0,0) whole plateaus of cells tie with the maximum."""
+    for k, (nq, nt, R, W, p) in enumerate([(200, 700, 1, 2, O.DEFAULT), (300, 300, 2, 3, (3, -2, 0, 0)), (150, 900, 1, 1, (2, -3, 5, 1)),
+                                           (260, 500, 4, 2, (1, -1, 0, 0))]):
+        q = rng.random_acgt(900 + k, 0, nq)
+        t = rng.random_acgt(900 + k, 1, nt)
+        t[nt // 2: nt // 2 + 60] = q[20:80]                     # one planted common stretch ...
+        if k % 2:
+            t[nt // 4: nt // 4 + 60] = q[20:80]                 # ... or two equally good ones
+        want, wi, wj = O.gotoh_end(t, q, p)                      # seq1 = T (columns j), seq2 = Q (rows i)
+        score, status, row, pos, endh = emu(q, t, R, 6, slack, W, 1, p)
+        assert (score, status, endh) == (want, 0, want)
+        assert (row, pos) == (wi, wj), (k, nq, nt, R, W, p)
 
 
 def test_edge_shapes(emu):

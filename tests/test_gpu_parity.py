@@ -314,3 +314,36 @@ def test_two_sided_sweep_against_oracle(api):
     b = rng.mutate(a[1000:1700], 901, 1, 0.03, 0.01)
     assert api.score(a, b, two_sided=1, rows=1) == O.gotoh_rolling(a, b)
     assert api.score(a, b, two_sided=1, rows=2, orient=1) == O.gotoh_rolling(a, b)
+
+
+def test_score_end_reports_the_end_cell_of_the_best_alignment(api):
+    """SURVEY.md 8(f) row 4 (new relative to the score-only reference): score + end cell, checked against the oracle's
+    rule -- the cell of main.cpp's H matrix holding the maximum, smallest j (seq1), then smallest i (seq2)."""
+    r = np.random.default_rng(77)
+    for k, (n, m, p) in enumerate([(1000, 1000, O.DEFAULT), (5000, 1200, (2, -3, 5, 1)), (700, 9000, (3, -2, 0, 0)),
+                                   (20000, 20000, O.DEFAULT), (3000, 3000, (1, -1, 0, 0)), (257, 129, (2, -1, 1, 3))]):
+        a = rng.random_acgt(600 + k, 0, n)
+        b = rng.random_acgt(600 + k, 1, m)
+        L = min(n, m) // 3
+        b[m // 2: m // 2 + L] = a[n // 4: n // 4 + L]                      # a planted common stretch
+        if k % 2:
+            b[: L // 2] = a[n // 4: n // 4 + L // 2]                         # and a second, shorter one
+        want = O.gotoh_end(a, b, p)
+        assert api.score_end(a, b, p) == want, (n, m, p)
+        assert api.score(a, b, p) == want[0]
+        info = api.last_run()
+    # identical sequences: the end cell is the last cell; unrelated single symbols: score 0 -> (0, 0)
+    a = rng.random_acgt(650, 0, 4000)
+    assert api.score_end(a, a) == (4000, 4000, 4000)
+    assert api.score_end(b"AAAA", b"CCCCCC") == (0, 0, 0)
+    assert api.score_end(b"", b"ACGT") == (0, 0, 0)
+    # other alphabets: at most four distinct bytes (re-encoded) and more (byte-compare kernel)
+    x = r.integers(0, 3, 900, dtype=np.uint8) + 65
+    y = np.concatenate([r.integers(0, 3, 300, dtype=np.uint8) + 65, x[100:500], r.integers(0, 3, 200, dtype=np.uint8) + 65])
+    assert api.score_end(x, y, (2, -3, 4, 1)) == O.gotoh_end(x, y, (2, -3, 4, 1))
+    x = r.integers(0, 20, 1500, dtype=np.uint8) + 65
+    y = np.concatenate([r.integers(0, 20, 400, dtype=np.uint8) + 65, x[200:900], r.integers(0, 20, 100, dtype=np.uint8) + 65])
+    assert api.score_end(x, y) == O.gotoh_end(x, y)
+    assert api.score_end("GATTACA", "GCATGCU") == O.gotoh_end(b"GATTACA", b"GCATGCU")
+    with pytest.raises(Exception):
+        api.score_end(np.full(2_000_000, 65, np.uint8), np.full(2_000_000, 65, np.uint8))   # match*min(n,m) >= 2^20
