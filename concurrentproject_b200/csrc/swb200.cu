@@ -943,6 +943,9 @@ int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const s
   if (b->npairs == 0) return SWB200_OK;
   const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
   const void* kern = swb::banded_kernel(mode);
+  // 4 CTAs of 35 KB static shared memory per SM: ask for the large shared-memory carve-out (latency hiding: the step
+  // loop is a chain of SHFL -> DPX -> SHFL, ncu shows short-scoreboard stalls on top)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   swb::BandedParams P{};
   P.a_words = b->q_words; P.b_words = b->t_words; P.a_len = b->q_len; P.b_len = b->t_len;
   P.a_stride = b->q_stride; P.b_stride = b->t_stride; P.npairs = b->npairs; P.band_lo = band_lo; P.scores = d_scores;

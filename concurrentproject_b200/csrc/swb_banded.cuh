@@ -4,15 +4,19 @@
 // band_lo <= j-i <= band_lo+63; out-of-band cells are H=E=F=0 and excluded from the max, i.e. main.cpp:57-63
 // evaluated on in-band cells only.  The reference has no banded mode.
 //
-// Geometry.  The 64 diagonals k = j-i of a pair are spread over 16 threads, 4 adjacent diagonals each:
-// the two with the parity of band_lo in one packed register set ("A"), the other two in a second ("B").
-// The sweep goes over anti-diagonals t = i+j; on one anti-diagonal only the diagonals with k = t (mod 2)
-// have a cell, so steps alternate A, B, A, B and every packed instruction does two useful cells.  A cell's
-// left neighbour is diagonal k-1 and its upper neighbour diagonal k+1, both on the previous anti-diagonal --
-// i.e. always in the OTHER register set of the same thread, except the outermost halves, which travel by one
-// __shfl_sync per step.  The diagonal neighbour is the cell's own register two steps ago.  Two pairs per warp.
-// Substitution scores: one PRMT per cell vector from two shared-memory rings filled cooperatively per pair,
-// a 4-byte score table per column symbol (as in the pair engine) and a PRMT selector per row pair.
+// Geometry.  The 64 diagonals k = j-i of a pair are spread over 16 threads.  Thread u holds four of them in two
+// packed register sets: A = (2u, 2u+32) and B = (2u+1, 2u+33) (offsets from band_lo; lo half, hi half).  The sweep
+// goes over anti-diagonals t = i+j; on one anti-diagonal only the diagonals with k = t (mod 2) have a cell, so steps
+// alternate A, B, A, B and every packed instruction does two useful cells.  A cell's left neighbour is diagonal k-1
+// and its upper neighbour diagonal k+1, both on the previous anti-diagonal: for set A the upper neighbours are the
+// thread's own B registers and the left neighbours are thread u-1's B registers -- BOTH halves at once, because the
+// two halves of a register are 32 diagonals apart -- so one __shfl_sync per step moves a whole register and no
+// half-word merging is needed (set B: left = own A, upper = thread u+1's A).  The seam between diagonal 31 and 32
+// rides on the same rotation: thread 15 sends (border, its B.lo) to thread 0, thread 0 sends (its A.hi, border) to
+// thread 15, one PRMT with a per-thread selector.  The diagonal neighbour is the cell's own register two steps
+// ago.  Two pairs per warp.  Substitution scores: one PRMT per cell vector from two shared-memory rings filled
+// cooperatively per pair, a 4-byte score table per column symbol (as in the pair engine) and a PRMT selector per
+// row pair (rows y and y-16: the hi half is 16 rows up and 16 columns right of the lo half).
 #pragma once
 #include "swb_engine.cuh"
 
@@ -34,9 +38,12 @@ struct BandedParams {
   int match, mismatch, gap_init, gap_ext;
 };
 
+// The two pairs of a warp read the same ring offsets in the same instruction: 16 words of padding put the
+// second pair's ring 16 banks away from the first one's, so the 2 x 16 threads hit 32 different banks
+// (without it every LDS of the step loop was a 2-way bank conflict and the LSU the bottleneck).
 struct BandedWarpSmem {
-  uint32_t tab[2][2 * kBandRing];   // [pair in warp][ring]: score table of column x at slot x & 127
-  uint32_t sel[2][2 * kBandRing];   // selector of rows (y, y-1) at slot y & 127
+  uint32_t tab[2][2 * kBandRing + 16];   // [pair in warp][ring]: score table of column x at slot x & 127
+  uint32_t sel[2][2 * kBandRing + 16];   // selector of rows (y, y-16) at slot y & 127
 };
 
 SWB_HD uint32_t packed_code(const uint64_t* words, int pos, int len) {
@@ -47,13 +54,16 @@ template <int MODE>
 SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_id, long long num_warps, BandedWarpSmem* sm) {
   const int lane = w.lane;
   const int u = lane & 15, grp = lane >> 4;
-  const int src_prev = grp * 16 + ((u + 15) & 15);     // A-step: value comes from thread u-1 (rotating)
-  const int src_next = grp * 16 + ((u + 1) & 15);      // B-step: value comes from thread u+1 (rotating)
+  const int src_prev = grp * 16 + ((u + 15) & 15);     // A-step: registers come from thread u-1 (rotating)
+  const int src_next = grp * 16 + ((u + 1) & 15);      // B-step: registers come from thread u+1 (rotating)
   const uint32_t nopen = pack2(-P.gap_init), next = pack2(-P.gap_ext);
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
   const uint32_t padw = padb * 0x01010101u;
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
   const uint32_t padsel = mk_sel16(4u, 4u);
+  // what a thread sends: its register as is, except at the seam (prmt(x, nopen, sel): bytes 0-3 = x, 4-7 = nopen)
+  const uint32_t sel_left = u == 15 ? 0x1054u : 0x3210u;   // thread 15 -> thread 0: (border, B.lo = diagonal 31)
+  const uint32_t sel_up = u == 0 ? 0x7632u : 0x3210u;      // thread 0 -> thread 15: (A.hi = diagonal 32, border)
   uint32_t* tab = sm->tab[grp];
   uint32_t* sel = sm->sel[grp];
   const long long ngroups = (P.npairs + 1) / 2;
@@ -74,8 +84,9 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
     // state of the 4 diagonals: H-open, E, F of register sets A and B; all cells start as border (H 0, E/F <= 0)
     uint32_t HoA = nopen, EA = nopen, FA = nopen, HoB = nopen, EB = nopen, FB = nopen;
     uint32_t best = 0;
-    // 0-based sequence positions of this thread's A.lo cell at double step h: row y = Y0 + h, column x = X0 + h
-    const int Y0 = I0 - 2 * u - 1, X0 = J0 + 2 * u - 1;
+    // 0-based sequence positions of this thread's A.lo cell at double step h: row y = Y0 + h, column x = X0 + h;
+    // A.hi: (y - 16, x + 16); B.lo: (y, x + 1); B.hi: (y - 16, x + 17)
+    const int Y0 = I0 - u - 1, X0 = J0 + u - 1;
 
     // ---- rings: everything pad, then selectors for rows [Yc-32, Yc) and tables for columns [Xc, Xc+32) of chunk 0
     const int Yc0 = I0 - 1, Xc0 = J0 - 1;                                  // thread 0's positions at h = 0
@@ -84,7 +95,7 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
     w.sync();
     for (int k = u; k < kChunk; k += 16) {
       const int y = Yc0 - kChunk + k;
-      const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 1, m));
+      const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 16, m));
       sel[y & (kBandRing - 1)] = sv; sel[(y & (kBandRing - 1)) + kBandRing] = sv;
       const int x = Xc0 + k;
       const uint32_t tv = table_word(packed_code(aw, x, n), padw, flip);
@@ -92,11 +103,11 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
     }
 
     for (int c = 0; c < nchunks; ++c) {
-      // ---- this chunk reads rows [Yc-30, Yc+32) and columns [Xc, Xc+64): add rows [Yc, Yc+32), columns [Xc+32, Xc+64)
+      // ---- this chunk reads rows [Yc-15, Yc+32) and columns [Xc, Xc+64): add rows [Yc, Yc+32), columns [Xc+32, Xc+64)
       const int Yc = Yc0 + c * kChunk, Xc = Xc0 + c * kChunk;
       for (int k = u; k < kChunk; k += 16) {
         const int y = Yc + k;
-        const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 1, m));
+        const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 16, m));
         sel[y & (kBandRing - 1)] = sv; sel[(y & (kBandRing - 1)) + kBandRing] = sv;
         const int x = Xc + kChunk + k;
         const uint32_t tv = table_word(packed_code(aw, x, n), padw, flip);
@@ -105,53 +116,43 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
       w.sync();
       const uint32_t* selp = sel + ((Y0 + c * kChunk) & (kBandRing - 1));
       const uint32_t* tabp = tab + ((X0 + c * kChunk) & (kBandRing - 1));
-      uint32_t T0 = tabp[0], T1 = tabp[1];
+      uint32_t a0 = tabp[0], b0 = tabp[16];
 #pragma unroll 4
       for (int h = 0; h < kChunk; ++h) {
         const uint32_t sv = selp[h];
-        const uint32_t T2 = tabp[h + 2];
-        const uint32_t sA = prmt(T0, T1, sv);        // A.lo: row y, column x ; A.hi: row y-1, column x+1
-        const uint32_t sB = prmt(T1, T2, sv);        // B.lo: row y, column x+1 ; B.hi: row y-1, column x+2
-        T0 = T1; T1 = T2;
-        // ---------------- anti-diagonal of set A: left neighbours are in B (lo: thread u-1's B.hi), upper = B as is
+        const uint32_t a1 = tabp[h + 1], b1 = tabp[h + 17];
+        const uint32_t sA = prmt(a0, b0, sv);        // A.lo: row y, column x ; A.hi: row y-16, column x+16
+        const uint32_t sB = prmt(a1, b1, sv);        // B.lo: row y, column x+1 ; B.hi: row y-16, column x+17
+        a0 = a1; b0 = b1;
+        // ---------------- anti-diagonal of set A: left neighbours = thread u-1's B, upper neighbours = own B
         {
-          uint32_t leftHo, h2;
+          uint32_t h2;
+          const uint32_t leftHo = w.shfl(prmt(HoB, nopen, sel_left), src_prev);
           if (MODE == 0) {
-            const uint32_t xs = (u == 15) ? nopen : prmt(HoB, EB, 0x7632u);       // (H-open, E) of B.hi
-            const uint32_t rv = w.shfl(xs, src_prev);
-            leftHo = prmt(rv, HoB, 0x5410u);
-            const uint32_t leftE = prmt(rv, EB, 0x5432u);
+            const uint32_t leftE = w.shfl(prmt(EB, nopen, sel_left), src_prev);
             const uint32_t E = addmax16x2(leftE, next, leftHo);
             const uint32_t F = addmax16x2(FB, next, HoB);
             const uint32_t d = add16x2(HoA, sA);
             h2 = max3relu16x2(d, E, F);
             EA = E; FA = F;
           } else {
-            const uint32_t xs = (u == 15) ? nopen : HoB;
-            const uint32_t rv = w.shfl(xs, src_prev);
-            leftHo = prmt(rv, HoB, 0x5432u);
             h2 = max16x2(addmaxrelu16x2(HoA, sA, leftHo), HoB);
           }
           HoA = add16x2(h2, nopen);
           best = max16x2(best, h2);
         }
-        // ---------------- anti-diagonal of set B: left = A as is, upper neighbours are in A (hi: thread u+1's A.lo)
+        // ---------------- anti-diagonal of set B: left neighbours = own A, upper neighbours = thread u+1's A
         {
-          uint32_t upHo, h2;
+          uint32_t h2;
+          const uint32_t upHo = w.shfl(prmt(HoA, nopen, sel_up), src_next);
           if (MODE == 0) {
-            const uint32_t xs = (u == 0) ? nopen : prmt(HoA, FA, 0x5410u);        // (H-open, F) of A.lo
-            const uint32_t rv = w.shfl(xs, src_next);
-            upHo = prmt(HoA, rv, 0x5432u);
-            const uint32_t upF = prmt(FA, rv, 0x7632u);
+            const uint32_t upF = w.shfl(prmt(FA, nopen, sel_up), src_next);
             const uint32_t E = addmax16x2(EA, next, HoA);
             const uint32_t F = addmax16x2(upF, next, upHo);
             const uint32_t d = add16x2(HoB, sB);
             h2 = max3relu16x2(d, E, F);
             EB = E; FB = F;
           } else {
-            const uint32_t xs = (u == 0) ? nopen : HoA;
-            const uint32_t rv = w.shfl(xs, src_next);
-            upHo = prmt(HoA, rv, 0x5432u);
             h2 = max16x2(addmaxrelu16x2(HoB, sB, HoA), upHo);
           }
           HoB = add16x2(h2, nopen);
@@ -172,7 +173,7 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
 
 #ifdef __CUDACC__
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) sw_banded_kernel(const __grid_constant__ BandedParams P) {
+__global__ void __launch_bounds__(256, 4) sw_banded_kernel(const __grid_constant__ BandedParams P) {
   __shared__ BandedWarpSmem sm[8];
   WarpCtx w{(int)(threadIdx.x & 31)};
   const int wi = (int)(threadIdx.x >> 5);
