@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -173,6 +174,8 @@ struct swb200_ctx {
   int sms = 0;
   std::mutex mu;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;        // host batch calls: kernels run here while own_stream copies the next chunk
+  std::vector<cudaEvent_t> chunk_events;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // grow-only device buffers
   uint8_t* d_ascii = nullptr; size_t ascii_cap = 0;
@@ -707,6 +710,7 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
   c->device = device;
   c->sms = prop.multiProcessorCount;
   SWB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  SWB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   SWB_CUDA(cudaEventCreate(&c->ev0));
   SWB_CUDA(cudaEventCreate(&c->ev1));
   SWB_CUDA(cudaMalloc(&c->d_result, 32 * sizeof(int)));
@@ -727,6 +731,8 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
   delete c;
 }
 
@@ -872,6 +878,89 @@ static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const lon
   return SWB200_OK;
 }
 
+// A contiguous range of pairs of a packed batch (all pointers already offset to its first pair).
+struct BatchView {
+  const uint64_t* q_words; const uint64_t* t_words; const int* q_len; const int* t_len;
+  long long q_stride, t_stride, npairs;
+  int max_short, max_long;      // of the WHOLE batch: every range of one batch runs the same kernel
+};
+
+static int check_batch_score(const BatchView& v, const swb200_params& p, int keep_order) {
+  if (keep_order) return fail(SWB200_ERR_ARG, "batch was packed in caller order (banded); re-pack with keep_order=0");
+  if (v.max_short > 1024)
+    return fail(SWB200_ERR_ARG, "batch kernel needs min(len1,len2) <= 1024 per pair; use swb200_score for long pairs");
+  if ((long long)p.match * v.max_short > 32767 - p.match - 1)
+    return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the batch kernel");
+  return SWB200_OK;
+}
+
+// Launches the batch kernel for one range; no synchronisation, no events.
+static int launch_batch_score(swb200_ctx* c, const BatchView& v, const swb200_params& p, const swb200_options& o,
+                              cudaStream_t s, int* d_scores, swb200_run_info* info) {
+  if (v.npairs == 0) return SWB200_OK;
+  int G = 8, per = 16;
+  if (v.max_short > 16 * 16) { G = 16; per = 32; }
+  if (v.max_short > 32 * 16) { G = 32; per = 64; }
+  int R = 16;
+  for (int k = swb::kNumBatchRowChoices - 1; k >= 0; --k)
+    if (swb::kBatchRowChoices[k] * per >= v.max_short) R = swb::kBatchRowChoices[k];
+  if (o.rows) R = o.rows;
+  if (R * per < v.max_short) return fail(SWB200_ERR_ARG, "rows too small for the longest short sequence");
+  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
+  const void* kern = swb::batch_kernel(R, mode, G);
+  if (!kern) return fail(SWB200_ERR_ARG, "no batch kernel for rows=" + std::to_string(R));
+  swb::BatchParams P{};
+  P.q_words = v.q_words; P.t_words = v.t_words; P.q_len = v.q_len; P.t_len = v.t_len;
+  P.q_stride = v.q_stride; P.t_stride = v.t_stride; P.npairs = v.npairs; P.scores = d_scores;
+  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
+  int per_sm = 0;
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  per_sm = std::max(per_sm, 1);
+  const long long groups = (v.npairs + (32 / G) - 1) / (32 / G);
+  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
+  void* args[] = {&P};
+  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
+  info->lanes = 16; info->linear = mode == 1; info->rows = R; info->config = 100 + G; info->ctas = (int)ctas;
+  info->warps = (int)ctas * 8; info->bands = 0; info->engine_launches += 1;
+  return SWB200_OK;
+}
+
+static int check_banded_score(const BatchView& v, const swb200_params& p, int keep_order, int band_lo, int band_hi) {
+  if (!keep_order) return fail(SWB200_ERR_ARG, "banded scoring needs a batch packed with keep_order=1");
+  if (band_hi - band_lo != swb::kBandWidth - 1) return fail(SWB200_ERR_ARG, "the banded kernel handles exactly 64 diagonals");
+  if ((long long)p.match * std::min(v.max_short, v.max_long) > 32767 - p.match - 1)
+    return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the banded kernel");
+  return SWB200_OK;
+}
+
+static int launch_banded_score(swb200_ctx* c, const BatchView& v, int band_lo, const swb200_params& p,
+                               const swb200_options& o, cudaStream_t s, int* d_scores, swb200_run_info* info) {
+  if (v.npairs == 0) return SWB200_OK;
+  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
+  const void* kern = swb::banded_kernel(mode);
+  // 4 CTAs of 35 KB static shared memory per SM: ask for the large shared-memory carve-out (latency hiding: the step
+  // loop is a chain of SHFL -> DPX -> SHFL, ncu shows short-scoreboard stalls on top)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  swb::BandedParams P{};
+  P.a_words = v.q_words; P.b_words = v.t_words; P.a_len = v.q_len; P.b_len = v.t_len;
+  P.a_stride = v.q_stride; P.b_stride = v.t_stride; P.npairs = v.npairs; P.band_lo = band_lo; P.scores = d_scores;
+  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
+  int per_sm = 0;
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  per_sm = std::max(per_sm, 1);
+  const long long groups = (v.npairs + 1) / 2;
+  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
+  void* args[] = {&P};
+  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
+  info->lanes = 16; info->linear = mode == 1; info->rows = 0; info->config = 200; info->ctas = (int)ctas;
+  info->warps = (int)ctas * 8; info->bands = swb::kBandWidth; info->engine_launches += 1;
+  return SWB200_OK;
+}
+
+static BatchView whole_batch(const swb200_batch* b) {
+  return BatchView{b->q_words, b->t_words, b->q_len, b->t_len, b->q_stride, b->t_stride, b->npairs, b->max_short, b->max_long};
+}
+
 int swb200_batch_score(swb200_batch* b, const swb200_params* pp, const swb200_options* oo, void* stream,
                        int* d_scores) {
   if (!b || !d_scores) return fail(SWB200_ERR_ARG, "bad batch arguments");
@@ -881,89 +970,46 @@ int swb200_batch_score(swb200_batch* b, const swb200_params* pp, const swb200_op
   const swb200_options o = oo ? *oo : swb200_options{};
   int rc;
   if ((rc = check_params(p))) return rc;
-  if (b->keep_order) return fail(SWB200_ERR_ARG, "batch was packed in caller order (banded); re-pack with keep_order=0");
-  if (b->max_short > 1024)
-    return fail(SWB200_ERR_ARG, "batch kernel needs min(len1,len2) <= 1024 per pair; use swb200_score for long pairs");
-  if ((long long)p.match * b->max_short > 32767 - p.match - 1)
-    return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the batch kernel");
+  const BatchView v = whole_batch(b);
+  if ((rc = check_batch_score(v, p, b->keep_order))) return rc;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   c->info = swb200_run_info{};
   c->info.cells = b->cells;
   if (b->npairs == 0) return SWB200_OK;
-  int G = 8, per = 16;
-  if (b->max_short > 16 * 16) { G = 16; per = 32; }
-  if (b->max_short > 32 * 16) { G = 32; per = 64; }
-  int R = 16;
-  for (int k = swb::kNumBatchRowChoices - 1; k >= 0; --k)
-    if (swb::kBatchRowChoices[k] * per >= b->max_short) R = swb::kBatchRowChoices[k];
-  if (o.rows) R = o.rows;
-  if (R * per < b->max_short) return fail(SWB200_ERR_ARG, "rows too small for the longest short sequence");
-  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
-  const void* kern = swb::batch_kernel(R, mode, G);
-  if (!kern) return fail(SWB200_ERR_ARG, "no batch kernel for rows=" + std::to_string(R));
-  swb::BatchParams P{};
-  P.q_words = b->q_words; P.t_words = b->t_words; P.q_len = b->q_len; P.t_len = b->t_len;
-  P.q_stride = b->q_stride; P.t_stride = b->t_stride; P.npairs = b->npairs; P.scores = d_scores;
-  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
-  int per_sm = 0;
-  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-  per_sm = std::max(per_sm, 1);
-  const long long groups = (b->npairs + (32 / G) - 1) / (32 / G);
-  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
-  void* args[] = {&P};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
-  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
+  if ((rc = launch_batch_score(c, v, p, o, s, d_scores, &c->info))) return rc;
   SWB_CUDA(cudaEventRecord(c->ev1, s));
   SWB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->info.lanes = 16; c->info.linear = mode == 1; c->info.rows = R; c->info.config = 100 + G; c->info.ctas = (int)ctas;
-  c->info.warps = (int)ctas * 8; c->info.bands = 0; c->info.engine_launches = 1; c->info.engine_ms = ms;
+  c->info.engine_ms = ms;
   return SWB200_OK;
 }
 
 int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const swb200_params* pp, const swb200_options* oo,
                               void* stream, int* d_scores) {
   if (!b || !d_scores) return fail(SWB200_ERR_ARG, "bad batch arguments");
-  if (!b->keep_order) return fail(SWB200_ERR_ARG, "banded scoring needs a batch packed with keep_order=1");
-  if (band_hi - band_lo != swb::kBandWidth - 1) return fail(SWB200_ERR_ARG, "the banded kernel handles exactly 64 diagonals");
   swb200_ctx* c = b->ctx;
   std::lock_guard<std::mutex> lk(c->mu);
   const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
   const swb200_options o = oo ? *oo : swb200_options{};
   int rc;
   if ((rc = check_params(p))) return rc;
-  if ((long long)p.match * std::min(b->max_short, b->max_long) > 32767 - p.match - 1)
-    return fail(SWB200_ERR_RANGE, "match * min(len) does not fit the 16-bit lanes of the banded kernel");
+  const BatchView v = whole_batch(b);
+  if ((rc = check_banded_score(v, p, b->keep_order, band_lo, band_hi))) return rc;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   c->info = swb200_run_info{};
   c->info.cells = b->cells;
   if (b->npairs == 0) return SWB200_OK;
-  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
-  const void* kern = swb::banded_kernel(mode);
-  // 4 CTAs of 35 KB static shared memory per SM: ask for the large shared-memory carve-out (latency hiding: the step
-  // loop is a chain of SHFL -> DPX -> SHFL, ncu shows short-scoreboard stalls on top)
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  swb::BandedParams P{};
-  P.a_words = b->q_words; P.b_words = b->t_words; P.a_len = b->q_len; P.b_len = b->t_len;
-  P.a_stride = b->q_stride; P.b_stride = b->t_stride; P.npairs = b->npairs; P.band_lo = band_lo; P.scores = d_scores;
-  P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
-  int per_sm = 0;
-  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-  per_sm = std::max(per_sm, 1);
-  const long long groups = (b->npairs + 1) / 2;
-  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
-  void* args[] = {&P};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
-  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
+  if ((rc = launch_banded_score(c, v, band_lo, p, o, s, d_scores, &c->info))) return rc;
   SWB_CUDA(cudaEventRecord(c->ev1, s));
   SWB_CUDA(cudaStreamSynchronize(s));
   float ms = 0;
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->info.lanes = 16; c->info.linear = mode == 1; c->info.rows = 0; c->info.config = 200; c->info.ctas = (int)ctas;
-  c->info.warps = (int)ctas * 8; c->info.bands = swb::kBandWidth; c->info.engine_launches = 1; c->info.engine_ms = ms;
+  c->info.engine_ms = ms;
   return SWB200_OK;
 }
 
@@ -997,37 +1043,90 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
     }
     cells += (long long)len1[k] * len2[k];
   }
-  uint8_t *d1 = nullptr, *d2 = nullptr;
-  long long *do1 = nullptr, *do2 = nullptr;
-  int *dl1 = nullptr, *dl2 = nullptr, *dsc = nullptr;
-  swb200_batch* b = nullptr;
-  cudaStream_t s;
+  // Pipeline: the pairs are cut into chunks of ~48 MB of sequence; own_stream copies chunk k+1 from the host while
+  // aux_stream packs and scores chunk k (the staging pool is sized for the whole batch, so chunks need no double
+  // buffering: every byte keeps its absolute position).  With pinned host buffers the call runs at PCIe speed.
+  const swb200_params pv = p ? *p : swb200_params{1, -1, 1, 1};
+  const swb200_options ov = opt ? *opt : swb200_options{};
+  if ((rc = check_params(pv))) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t sc = c->own_stream, sk = c->aux_stream;
+  const size_t np = (size_t)npairs;
+  const long long q_stride = std::max(1, (max_short + 31) / 32) + (banded ? 2 : 0);
+  const long long t_stride = std::max(1, (max_long + 31) / 32) + 2;      // +2: the kernel prefetches one word past the end
+  if ((rc = grow(c->hb_seq1, c->hb_seq1_cap, (size_t)bytes1 + 16, false, sc)) || (rc = grow(c->hb_seq2, c->hb_seq2_cap, (size_t)bytes2 + 16, false, sc)) ||
+      (rc = grow(c->hb_off1, c->hb_off1_cap, np, false, sc)) || (rc = grow(c->hb_off2, c->hb_off2_cap, np, false, sc)) ||
+      (rc = grow(c->hb_len1, c->hb_len1_cap, np, false, sc)) || (rc = grow(c->hb_len2, c->hb_len2_cap, np, false, sc)) ||
+      (rc = grow(c->hb_scores, c->hb_scores_cap, np, false, sc)) ||
+      (rc = grow(c->hb_qw, c->hb_qw_cap, np * q_stride, false, sc)) || (rc = grow(c->hb_tw, c->hb_tw_cap, np * t_stride, false, sc)) ||
+      (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, sc)) || (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, sc))) return rc;
+  const BatchView all{c->hb_qw, c->hb_tw, c->hb_ql, c->hb_tl, q_stride, t_stride, npairs, max_short, max_long};
+  if ((rc = banded ? check_banded_score(all, pv, 1, band_lo, band_hi) : check_batch_score(all, pv, 0))) return rc;
+
+  // chunk boundaries and the byte range each chunk touches in the two host buffers
+  struct Chunk { long long k0, k1, lo1, hi1, lo2, hi2; };
+  std::vector<Chunk> chunks;
   {
-    std::lock_guard<std::mutex> lk(c->mu);
-    SWB_CUDA(cudaSetDevice(c->device));
-    s = c->own_stream;
-    const size_t np = (size_t)npairs;
-    if ((rc = grow(c->hb_seq1, c->hb_seq1_cap, (size_t)bytes1 + 16, false, s)) || (rc = grow(c->hb_seq2, c->hb_seq2_cap, (size_t)bytes2 + 16, false, s)) ||
-        (rc = grow(c->hb_off1, c->hb_off1_cap, np, false, s)) || (rc = grow(c->hb_off2, c->hb_off2_cap, np, false, s)) ||
-        (rc = grow(c->hb_len1, c->hb_len1_cap, np, false, s)) || (rc = grow(c->hb_len2, c->hb_len2_cap, np, false, s)) ||
-        (rc = grow(c->hb_scores, c->hb_scores_cap, np, false, s))) return rc;
-    d1 = c->hb_seq1; d2 = c->hb_seq2; do1 = c->hb_off1; do2 = c->hb_off2; dl1 = c->hb_len1; dl2 = c->hb_len2; dsc = c->hb_scores;
-    SWB_CUDA(cudaMemcpyAsync(d1, seq1_all, (size_t)bytes1, cudaMemcpyHostToDevice, s));
-    SWB_CUDA(cudaMemcpyAsync(d2, seq2_all, (size_t)bytes2, cudaMemcpyHostToDevice, s));
-    SWB_CUDA(cudaMemcpyAsync(do1, off1, npairs * sizeof(long long), cudaMemcpyHostToDevice, s));
-    SWB_CUDA(cudaMemcpyAsync(do2, off2, npairs * sizeof(long long), cudaMemcpyHostToDevice, s));
-    SWB_CUDA(cudaMemcpyAsync(dl1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
-    SWB_CUDA(cudaMemcpyAsync(dl2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    const long long target = 48LL << 20;
+    Chunk cur{0, 0, LLONG_MAX, 0, LLONG_MAX, 0};
+    long long acc = 0;
+    for (long long k = 0; k < npairs; ++k) {
+      cur.lo1 = std::min(cur.lo1, off1[k]); cur.hi1 = std::max(cur.hi1, off1[k] + len1[k]);
+      cur.lo2 = std::min(cur.lo2, off2[k]); cur.hi2 = std::max(cur.hi2, off2[k] + len2[k]);
+      acc += (long long)len1[k] + len2[k];
+      if ((acc >= target && k + 1 - cur.k0 >= 1024) || k + 1 == npairs) {
+        cur.k1 = k + 1;
+        chunks.push_back(cur);
+        cur = Chunk{k + 1, 0, LLONG_MAX, 0, LLONG_MAX, 0};
+        acc = 0;
+      }
+    }
   }
-  rc = batch_pack_impl(c, d1, do1, dl1, d2, do2, dl2, npairs, max_short, max_long, cells, banded, true, s, &b);
-  if (rc == SWB200_OK) rc = banded ? swb200_batch_score_banded(b, band_lo, band_hi, p, opt, s, dsc) : swb200_batch_score(b, p, opt, s, dsc);
-  if (rc == SWB200_OK) {
-    cudaError_t e = cudaMemcpyAsync(scores_out, dsc, npairs * sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) rc = fail(SWB200_ERR_CUDA, std::string("batch result copy: ") + cudaGetErrorString(e));
+  while (c->chunk_events.size() < chunks.size() + 1) {
+    cudaEvent_t e;
+    SWB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->chunk_events.push_back(e);
   }
-  swb200_batch_free(b);
-  return rc;
+  c->info = swb200_run_info{};
+  c->info.cells = cells;
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_off1, off1, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_off2, off2, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_len1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_len2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
+  bool first = true;
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk& ch = chunks[ci];
+    if (ch.hi1 > ch.lo1) SWB_CUDA(cudaMemcpyAsync(c->hb_seq1 + ch.lo1, seq1_all + ch.lo1, (size_t)(ch.hi1 - ch.lo1), cudaMemcpyHostToDevice, sc));
+    if (ch.hi2 > ch.lo2) SWB_CUDA(cudaMemcpyAsync(c->hb_seq2 + ch.lo2, seq2_all + ch.lo2, (size_t)(ch.hi2 - ch.lo2), cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaEventRecord(c->chunk_events[ci], sc));
+    SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
+    if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
+    const long long nk = ch.k1 - ch.k0;
+    const long long total = nk * (q_stride + t_stride);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);
+    swb::launch_pack_batch(c->hb_seq1, c->hb_off1 + ch.k0, c->hb_len1 + ch.k0, c->hb_seq2, c->hb_off2 + ch.k0, c->hb_len2 + ch.k0, nk,
+                           q_stride, t_stride, c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0,
+                           c->hb_tl + ch.k0, banded ? 1 : 0, c->d_result, blocks, sk);
+    SWB_CUDA(cudaGetLastError());
+    c->info.aux_launches += 1;
+    const BatchView v{c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0, c->hb_tl + ch.k0,
+                      q_stride, t_stride, nk, max_short, max_long};
+    rc = banded ? launch_banded_score(c, v, band_lo, pv, ov, sk, c->hb_scores + ch.k0, &c->info)
+                : launch_batch_score(c, v, pv, ov, sk, c->hb_scores + ch.k0, &c->info);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
+  }
+  SWB_CUDA(cudaEventRecord(c->ev1, sk));
+  SWB_CUDA(cudaMemcpyAsync(scores_out, c->hb_scores, npairs * sizeof(int), cudaMemcpyDeviceToHost, sk));
+  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(int), cudaMemcpyDeviceToHost, sk));
+  SWB_CUDA(cudaStreamSynchronize(sk));
+  SWB_CUDA(cudaStreamSynchronize(sc));
+  float ms = 0;
+  SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->info.engine_ms = ms;          // first pack to last kernel, copies of later chunks overlapped
+  if (c->h_result[1] & swb::STATUS_BAD_SYMBOL) return fail(SWB200_ERR_ALPHABET, "batch input contains bytes other than A,C,G,T");
+  return SWB200_OK;
 }
 
 int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
