@@ -158,6 +158,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
+    committed under profiles/ (only the bench default has one); None otherwise."""
+    if workload != "cfg2":
+        return None
+    try:
+        d = json.load(open(ROOT / "profiles" / "r01_ncu_summary.json"))
+        return int(d["r01_cfg2_final2.ncu-rep"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,8 +265,10 @@ def run_ours(args):
                     "call": "SmithWatermanScoreCUDA(host bytes) via libswb200.so C ABI, wall clock"},
             "gpu_launches": launches,
             "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                         "frac": round(achieved / peak, 4), "traffic": None,
-                         "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); peak = 148 SM x {f_mhz} MHz x "
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
+                         "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); traffic = DRAM bytes per launch "
+                                 f"from the committed ncu capture (profiles/r01_ncu_summary.json), algorithmic input is {(n + m) // 4} bytes, "
+                                 f"the boundary rows of the bands live in L2; peak = 148 SM x {f_mhz} MHz x "
                                  f"L={DPX_LANE_INSTR_PER_CLK_PER_SM:.0f} DPX lane-instr/clk/SM (measured, bench/intpeak.cu) x V={vwidth} / 7 "
                                  "instr per cell vector (SURVEY.md 8d); not an HBM- or tensor-bound kernel"},
             "cpu_baseline": {"value": round(cpu_g, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
