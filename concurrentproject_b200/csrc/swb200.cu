@@ -400,6 +400,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   if ((pl.mode == 3 || pl.mode == 4) && !rebase_is_safe(p, pl.R))
     return fail(SWB200_ERR_ARG, "re-based lanes are not safe for these scoring parameters / row count");
   if (NB >= (1 << 18)) return fail(SWB200_ERR_ARG, "sequence too long for this row count (bands >= 2^18)");
+  if (LT >= (1LL << 30)) return fail(SWB200_ERR_ARG, "streamed sequence too long (>= 2^30)");       // 32-bit step arithmetic
   if (ring && NB > 1 && ring->call_epoch == 0) return fail(SWB200_ERR_ARG, "ring epoch exhausted; create a new ring");
   // two-sided sweep: rows [0, mid) forward, rows [mid, LQ) reversed (with pad rows in front so that the reversed
   // half also ends exactly on a band boundary); mid is a multiple of the band height
@@ -1068,14 +1069,16 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
   struct Chunk { long long k0, k1, lo1, hi1, lo2, hi2; };
   std::vector<Chunk> chunks;
   {
-    const long long target = 48LL << 20;
+    const char* ov_chunk = getenv("SWB200_BATCH_CHUNK_BYTES");       // tests: force many small chunks
+    const long long target = ov_chunk ? std::max(1LL, atoll(ov_chunk)) : 48LL << 20;
+    const long long min_pairs = ov_chunk ? 1 : 1024;
     Chunk cur{0, 0, LLONG_MAX, 0, LLONG_MAX, 0};
     long long acc = 0;
     for (long long k = 0; k < npairs; ++k) {
       cur.lo1 = std::min(cur.lo1, off1[k]); cur.hi1 = std::max(cur.hi1, off1[k] + len1[k]);
       cur.lo2 = std::min(cur.lo2, off2[k]); cur.hi2 = std::max(cur.hi2, off2[k] + len2[k]);
       acc += (long long)len1[k] + len2[k];
-      if ((acc >= target && k + 1 - cur.k0 >= 1024) || k + 1 == npairs) {
+      if ((acc >= target && k + 1 - cur.k0 >= min_pairs) || k + 1 == npairs) {
         cur.k1 = k + 1;
         chunks.push_back(cur);
         cur = Chunk{k + 1, 0, LLONG_MAX, 0, LLONG_MAX, 0};

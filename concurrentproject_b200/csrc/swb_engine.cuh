@@ -171,9 +171,10 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
   const uint32_t padw = padb * 0x01010101u;
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
-  const long long LT = P.LT;
+  const int LT = (int)P.LT;            // step arithmetic is 32-bit (the host refuses LT >= 2^30); only ring indices,
+                                       // which count steps over all rounds, are 64-bit
   constexpr int STEP_ALIGN = RB ? kRebaseBlock : kChunk;   // RB: base blocks of consecutive bands must not share a slot
-  const long long nsteps = ((LT + SKEW + STEP_ALIGN - 1) / STEP_ALIGN) * STEP_ALIGN;
+  const int nsteps = ((LT + SKEW + STEP_ALIGN - 1) / STEP_ALIGN) * STEP_ALIGN;
   uint32_t best0 = 0, best1 = 0;
   int base = 0, best_abs = 0;          // RB only
   uint32_t floorw = 0;                 // RB only: packed max(-base, -30000)
@@ -198,7 +199,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a
     // ring is one continuous stream and back-pressure spans band boundaries; the full-length ext
     // stream restarts at 0 every band (safe: see DESIGN.md, hand-off protocol).
-    const long long sbase = (band / P.ring_total) * nsteps;
+    const long long sbase = (band / P.ring_total) * (long long)nsteps;
     const long long in_base = first_local ? 0 : sbase, out_base = last_local ? 0 : sbase;
 
     // ---- per-band constants: PRMT selectors of this thread's 2*R rows
@@ -232,7 +233,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     for (int k = 0; k < 2 * kTabRing / 32; ++k) sm->tab[k * 32 + lane] = padw;
     w.sync();
     {
-      const long long q = lane;
+      const int q = lane;
       uint32_t c = 4;
       if (q < LT) c = (uint32_t)(P.t_packed[q >> 5] >> (2 * (q & 31))) & 3u;
       const uint32_t tw = table_word(c, padw, flip);
@@ -258,14 +259,14 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       if (lane == 0) yold = v0;
     }
 
-    for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
+    for (int i0 = 0; i0 < nsteps; i0 += kChunk) {
 #if SWB_DEVICE_CODE
       const long long tp0 = P.prof ? clock64() : 0;
       const long long bud0 = wt.budget;
 #endif
       // (a) substitution tables for T positions [i0+32, i0+64); fetch the word after that
       {
-        const long long q = i0 + kChunk + lane;
+        const int q = i0 + kChunk + lane;
         uint32_t c = 4;
         if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
         const uint32_t tw = table_word(c, padw, flip);
@@ -302,7 +303,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       }
       // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): wait for the producer
       {
-        const long long q = i0 + SLACK + lane;
+        const int q = i0 + SLACK + lane;
         uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
         if (!zero_src) {                                                  // warp-uniform branch
           const bool need = q < LT;
@@ -339,7 +340,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       const long long tp1 = P.prof ? clock64() : 0;
 #endif
 
-      const uint32_t* tabp = sm->tab + ((i0 - (long long)SK * lane) & (kTabRing - 1));
+      const uint32_t* tabp = sm->tab + ((i0 - SK * lane) & (kTabRing - 1));
       const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
       uint2* outp = out + ((out_base + i0) & out_mask);
       const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
@@ -474,8 +475,9 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
   const uint32_t padw = GEN ? 0x200u : padb * 0x01010101u;       // GEN: 0x200 equals no byte and no pad row (0x100)
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
   const int s_match = P.match + P.gap_init, s_mismatch = P.mismatch + P.gap_init;
-  const long long LT = P.LT;
-  const long long nsteps = ((LT + SKEW + kChunk - 1) / kChunk) * kChunk;
+  const int LT = (int)P.LT;            // step arithmetic is 32-bit (the host refuses LT >= 2^30); only ring indices,
+                                       // which count steps over all rounds, are 64-bit
+  const int nsteps = ((LT + SKEW + kChunk - 1) / kChunk) * kChunk;
   int best0 = 0, best1 = 0;
   Waiter wt{P.spin_limit, false};
 
@@ -498,7 +500,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     // Inner rings are indexed by the CUMULATIVE producer step over all rounds (sbase + step), so a
     // ring is one continuous stream and back-pressure spans band boundaries; the full-length ext
     // stream restarts at 0 every band (safe: see DESIGN.md, hand-off protocol).
-    const long long sbase = (band / P.ring_total) * nsteps;
+    const long long sbase = (band / P.ring_total) * (long long)nsteps;
     const long long in_base = first_local ? 0 : sbase, out_base = last_local ? 0 : sbase;
 
     uint32_t sel[R];
@@ -515,14 +517,14 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
     int up_prev = nopen, xsH = nopen, xsF = nopen, yoldH = nopen, yoldF = nopen;
     int bestkey = 0, rec_h = 0, rec_key = 0;         // TRACK only
-    long long rec_win = 0;
+    int rec_win = 0;
 
     w.sync();
 #pragma unroll
     for (int k = 0; k < 2 * kTabRing / 32; ++k) sm->tab[k * 32 + lane] = padw;
     w.sync();
     {
-      const long long q = lane;
+      const int q = lane;
       uint32_t tw;
       if (GEN) tw = q < LT ? (uint32_t)P.t_bytes[q] : padw;
       else {
@@ -548,9 +550,9 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       if (lane == 0) { yoldH = (int)h0; yoldF = (int)f0; }
     }
 
-    for (long long i0 = 0; i0 < nsteps; i0 += kChunk) {
+    for (int i0 = 0; i0 < nsteps; i0 += kChunk) {
       {
-        const long long q = i0 + kChunk + lane;
+        const int q = i0 + kChunk + lane;
         uint32_t tw;
         if (GEN) tw = (uint32_t)twpref;
         else {
@@ -564,7 +566,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
         else twpref = (q + kChunk < LT) ? ld_early_u64(P.t_packed + ((q + kChunk) >> 5)) : 0ull;
       }
       {
-        const long long q = i0 + SLACK + lane;
+        const int q = i0 + SLACK + lane;
         uint32_t vH = (uint32_t)nopen, vF = (uint32_t)nopen;
         if (!zero_src) {
           const bool need = q < LT;
@@ -591,7 +593,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       }
       w.sync();
 
-      const uint32_t* tabp = sm->tab + ((i0 - (long long)SK * lane) & (kTabRing - 1));
+      const uint32_t* tabp = sm->tab + ((i0 - SK * lane) & (kTabRing - 1));
       const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
       uint2* outp = out + 2 * ((out_base + i0) & out_mask);
       const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
@@ -659,13 +661,13 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
         const bool upd = hb > rec_h;
         rec_h = upd ? hb : rec_h;
         rec_key = upd ? bestkey : rec_key;
-        rec_win = upd ? (i0 & ~127LL) : rec_win;
+        rec_win = upd ? (i0 & ~127) : rec_win;
       }
     }
     if (TRACK) {
       // this lane's first best cell: step -> T position (lane l is SK*l positions behind lane 0), row in Q
-      const long long step = rec_win + 127 - ((rec_key >> 4) & 127);
-      const int pos = (int)(step - (long long)SK * lane);
+      const int step = rec_win + 127 - ((rec_key >> 4) & 127);
+      const int pos = step - SK * lane;
       const int row = (int)(band * (32LL * R) + (long long)lane * R + (15 - (rec_key & 15)));
       const int hmax = w.reduce_max(rec_h);
       const int pmin = -w.reduce_max(rec_h == hmax ? -pos : -0x7fffffff);

@@ -59,3 +59,25 @@ def test_search_one_query_against_a_database():
     want = np.array([O.gotoh_rolling(q, d) for d in db], dtype=np.int32)
     got = fasta.search(q, db, min_bucket=64)
     assert np.array_equal(got, want) and int(np.argmax(got)) == 123
+
+
+def test_host_batch_call_pipelines_chunks(monkeypatch):
+    """swb200_score_batch cuts the batch into chunks (copy of chunk k+1 overlaps packing and scoring chunk k):
+    force ~60 chunks with ragged lengths, a shared sequence (every pair reads the same seq1 bytes) and offsets that
+    are not monotone."""
+    from concurrentproject_b200 import api, fasta
+    monkeypatch.setenv("SWB200_BATCH_CHUNK_BYTES", "20000")
+    s1, s2 = _ragged(21, 1500, 250, 900)
+    assert np.array_equal(api.score_batch(s1, s2), O.gotoh_batch(s1, s2))
+    db = [bytes(rng.random_acgt(22, k, 30 + (k * 53) % 700)) for k in range(900)]
+    q = bytes(rng.mutate(db[500][5:140], 22, 7000, 0.05, 0.02))
+    want = np.array([O.gotoh_rolling(q, d) for d in db], dtype=np.int32)
+    assert np.array_equal(fasta.search(q, db, min_bucket=100000), want)          # seq1 offsets all zero
+    perm = np.random.default_rng(3).permutation(len(s1))                          # non-monotone offsets
+    f1, o1, l1 = api._flatten(s1); f2, o2, l2 = api._flatten(s2)
+    got = api.score_batch_flat(f1, o1[perm], l1[perm], f2, o2[perm], l2[perm])
+    assert np.array_equal(got, O.gotoh_batch(s1, s2)[perm])
+    lo, hi = -32, 31
+    a = [bytes(rng.random_acgt(23, k, 400 + k % 50)) for k in range(300)]
+    b = [bytes(rng.mutate(x, 23, 1000 + k, 0.05, 0.01)) for k, x in enumerate(a)]
+    assert np.array_equal(api.score_banded_batch(a, b, lo, hi), O.gotoh_banded_batch(a, b, lo, hi))
