@@ -128,20 +128,27 @@ __global__ void encode_t_rev_kernel(const uint8_t* __restrict__ src, long long n
 // half at T position p; f1[p' + skew] = the same of the reversed half at reversed position p'.  A crossing path
 // passes lattice point (mid, x): best score ending there (forward) + best score starting there (reversed); a
 // vertical gap that straddles the row was opened twice, hence the + gap_init - gap_ext variant (Myers-Miller).
+// Re-based lanes: the entries are relative to the base their warp published for the 256-step block (b0 / b1, null
+// for plain 16-bit lanes).
 __global__ void combine_two_sided_kernel(const uint2* __restrict__ f0, const uint2* __restrict__ f1, long long LT, int skew,
-                                         int linear, int gap_init, int gap_ext, int* result) {
+                                         int linear, int gap_init, int gap_ext, const uint2* __restrict__ b0,
+                                         const uint2* __restrict__ b1, int* result) {
   int best = 0;
   for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x <= LT; x += (long long)gridDim.x * blockDim.x) {
     int Hf = 0, Ff = -1000000, Hb = 0, Fb = -1000000;
     if (x >= 1) {
-      const uint32_t e = f0[x - 1 + skew].x;
-      if (linear) Hf = (int)(short)(e >> 16) + gap_init;
-      else { Hf = (int)(short)(e & 0xFFFFu) + gap_init; Ff = (int)(short)(e >> 16); }
+      const long long j = x - 1 + skew;
+      const uint32_t e = f0[j].x;
+      const int base = b0 ? (int)b0[j >> 8].x : 0;
+      if (linear) Hf = (int)(short)(e >> 16) + gap_init + base;
+      else { Hf = (int)(short)(e & 0xFFFFu) + gap_init + base; Ff = (int)(short)(e >> 16) + base; }
     }
     if (x <= LT - 1) {
-      const uint32_t e = f1[(LT - 1 - x) + skew].x;
-      if (linear) Hb = (int)(short)(e >> 16) + gap_init;
-      else { Hb = (int)(short)(e & 0xFFFFu) + gap_init; Fb = (int)(short)(e >> 16); }
+      const long long j = (LT - 1 - x) + skew;
+      const uint32_t e = f1[j].x;
+      const int base = b1 ? (int)b1[j >> 8].x : 0;
+      if (linear) Hb = (int)(short)(e >> 16) + gap_init + base;
+      else { Hb = (int)(short)(e & 0xFFFFu) + gap_init + base; Fb = (int)(short)(e >> 16) + base; }
     }
     int v = Hf + Hb;
     if (!linear) v = max(v, Ff + Fb + gap_init - gap_ext);
@@ -347,8 +354,9 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
       if (o.rows && o.rows != R) continue;
       const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
       if (e < best) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
-      // two-sided: only plain 16-bit lanes, at least 4 bands per half
-      if (allow_two_sided && pl.mode <= 1 && o.two_sided >= 0 && LQ >= 8LL * swb::rows_per_band(R, pl.mode)) {
+      // two-sided: packed 16-bit lanes (plain or re-based), at least 4 bands per half
+      if (allow_two_sided && (pl.mode <= 1 || pl.mode == 3 || pl.mode == 4) && o.two_sided >= 0 &&
+          LQ >= 8LL * swb::rows_per_band(R, pl.mode)) {
         const double e2 = estimate(LQ, LT, pl.mode, R, ci, sms, true);
         if (e2 < 0.97 * best || (o.two_sided > 0 && (e2 < best || !pl.two_sided))) { best = std::min(best, e2); pl.R = R; pl.config = ci; pl.two_sided = true; }
       }
@@ -514,8 +522,12 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaEventRecord(c->ev0, s));
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
   if (ts) {
-    combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(c->d_final, c->d_final + 2 * (size_t)ext_len, LT, skew, pl.mode == 1,
-                                                        p.gap_init, p.gap_ext, c->d_result);
+    // re-based lanes: the final bands' bases sit in the second half of each buffer, region (band & 3) of four
+    const bool rb = pl.mode == 3 || pl.mode == 4;
+    const uint2* bf = rb ? c->d_final + (size_t)ext_len + (size_t)((NB0 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
+    const uint2* bb = rb ? c->d_final + 3 * (size_t)ext_len + (size_t)((NB1 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
+    combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(c->d_final, c->d_final + 2 * (size_t)ext_len, LT, skew,
+                                                        pl.mode == 1 || pl.mode == 4, p.gap_init, p.gap_ext, bf, bb, c->d_result);
     c->info.aux_launches += 1;
   }
   if (track) {

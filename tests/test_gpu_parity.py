@@ -279,6 +279,11 @@ def test_rebased_16_bit_lanes(api, config):
     assert api.score(a, b, lanes=32) == want
     p = (3, -2, 4, 2)                                        # other parameters, still inside the re-base safety bound for R=4
     assert api.score(a, b, p, lanes=16, rebase=1, rows=4, config=config) == O.gotoh_mt(a, b, p)
+    # two-sided sweep in re-based lanes: the level is far above 32767 where the two halves meet
+    for rows, no_linear in ((4, False), (8, True)):
+        assert api.score(a, b, lanes=16, rebase=1, rows=rows, config=config, no_linear=no_linear, two_sided=1) == want
+        info = api.last_run()
+        assert (info["two_sided"], info["rebased"]) == (1, 1)
 
 
 def test_rebased_lanes_refuse_unsafe_parameters(api):
@@ -310,6 +315,12 @@ def test_two_sided_sweep_against_oracle(api):
                     assert api.last_run()["two_sided"] == 1
                     assert got == want, (name, p, rows, config, no_linear, got, want)
                     assert api.score(b, a, p, rows=rows, config=config, no_linear=no_linear, two_sided=1) == want
+            if p[0] + max(p[2], p[3]) <= 5:        # re-based lanes (safe for these parameters at these row counts)
+                for rows, config in ((1, 1), (4, 3), (2, 2)):
+                    got = api.score(a, b, p, rows=rows, config=config, rebase=1, two_sided=1, no_linear=(rows == 4))
+                    info = api.last_run()
+                    assert (info["two_sided"], info["rebased"]) == (1, 1)
+                    assert got == want, (name, p, rows, config, got, want)
     # the middle need not be the middle of the alignment: very unequal lengths, striped sequence chosen by orient
     b = rng.mutate(a[1000:1700], 901, 1, 0.03, 0.01)
     assert api.score(a, b, two_sided=1, rows=1) == O.gotoh_rolling(a, b)
