@@ -14,11 +14,10 @@ to the GPU kernels:
                          (swb200_score_ex), which compares bytes exactly like main.cpp:60;
 * ``search``          -- one query against every record of a database.
 
-Flattening of bucket k+1 on the host overlaps the GPU work of bucket k (two host threads; ctypes drops the
-GIL during the C call).  There is no CPU scoring path here."""
+The residues are uploaded to HBM once per call (torch is the plumbing for device memory); a bucket only ships its
+offsets and lengths and is packed and scored where the bytes already are.  There is no CPU scoring path here."""
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import List, Sequence, Tuple
 
@@ -137,7 +136,7 @@ def plan_buckets(len1: np.ndarray, len2: np.ndarray, acgt_only: np.ndarray, min_
 
 
 def _gather(flat: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, ids: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Bytes of records ``ids`` back to back (vectorised ragged gather)."""
+    """Bytes of records ``ids`` back to back (vectorised ragged gather; host utility, not on the scoring path)."""
     lens = lengths[ids].astype(np.int32)
     total = int(lens.sum())
     new_off = np.zeros(len(ids), dtype=np.int64)
@@ -150,14 +149,32 @@ def _gather(flat: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, ids: np.
 
 
 def _record_is_acgt(flat: np.ndarray, offsets: np.ndarray, lengths: np.ndarray) -> np.ndarray:
-    bad = (~_IS_ACGT[flat]).astype(np.int64)
-    csum = np.concatenate(([0], np.cumsum(bad)))
-    return (csum[offsets + lengths] - csum[offsets]) == 0
+    """Host version of the per-record alphabet check (tests; small inputs)."""
+    bad = np.flatnonzero(~_IS_ACGT[flat])
+    ok = np.ones(len(offsets), dtype=bool)
+    if bad.size:
+        ok[np.searchsorted(offsets + lengths, bad, side="right")] = False
+    return ok
+
+
+def _device_records(rec: FastaRecords, torch, device):
+    """Residues of all records in HBM (uploaded once per call) and which records are pure A,C,G,T."""
+    flat = torch.from_numpy(rec.flat if rec.flat.size else np.zeros(1, np.uint8)).to(device, non_blocking=False)
+    ok = np.ones(len(rec), dtype=bool)
+    if rec.flat.size:
+        f = flat[:rec.flat.size]
+        bad = torch.nonzero(~((f == 65) | (f == 67) | (f == 71) | (f == 84))).flatten().cpu().numpy()
+        if bad.size:
+            ok[np.searchsorted(rec.offsets + rec.lengths, bad, side="right")] = False
+    return flat, ok
 
 
 def score_records(a: FastaRecords, ia: np.ndarray, b: FastaRecords, ib: np.ndarray,
-                  params: Sequence[int] = api.DEFAULT_PARAMS, *, min_bucket: int = 512) -> np.ndarray:
-    """Score pair k = (a[ia[k]], b[ib[k]]) for index arrays ia, ib.  Returns int32 scores in pair order."""
+                  params: Sequence[int] = api.DEFAULT_PARAMS, *, min_bucket: int = 512, device: int = 0) -> np.ndarray:
+    """Score pair k = (a[ia[k]], b[ib[k]]) for index arrays ia, ib.  Returns int32 scores in pair order.
+    The residues go to HBM once; every bucket then only ships its offsets and lengths and is packed and scored
+    in place (swb200_batch_pack_device / swb200_batch_score)."""
+    import torch
     ia = np.asarray(ia, dtype=np.int64)
     ib = np.asarray(ib, dtype=np.int64)
     if ia.shape != ib.shape:
@@ -165,27 +182,40 @@ def score_records(a: FastaRecords, ia: np.ndarray, b: FastaRecords, ib: np.ndarr
     scores = np.zeros(len(ia), dtype=np.int32)
     if len(ia) == 0:
         return scores
-    ok_a = _record_is_acgt(a.flat, a.offsets, a.lengths.astype(np.int64))
-    ok_b = _record_is_acgt(b.flat, b.offsets, b.lengths.astype(np.int64))
-    buckets = plan_buckets(a.lengths[ia], b.lengths[ib], ok_a[ia] & ok_b[ib], min_bucket)
-
-    def prepare(bk: Bucket):
-        if bk.kind != "batch":
-            return None
-        return _gather(a.flat, a.offsets, a.lengths, ia[bk.index]) + _gather(b.flat, b.offsets, b.lengths, ib[bk.index])
-
-    with ThreadPoolExecutor(max_workers=1) as pool:
-        nxt = pool.submit(prepare, buckets[0])
-        for k, bk in enumerate(buckets):
-            prepared = nxt.result()
-            if k + 1 < len(buckets):
-                nxt = pool.submit(prepare, buckets[k + 1])
+    if not torch.cuda.is_available():
+        raise RuntimeError("concurrentproject_b200.fasta needs a CUDA device; there is no CPU scoring path")
+    dev = torch.device("cuda", device)
+    ctx = api.Context(device)
+    try:
+        fa, ok_a = _device_records(a, torch, dev)
+        fb, ok_b = (fa, ok_a) if b is a else _device_records(b, torch, dev)
+        l1, l2 = a.lengths[ia].astype(np.int32), b.lengths[ib].astype(np.int32)
+        o1, o2 = a.offsets[ia].astype(np.int64), b.offsets[ib].astype(np.int64)
+        buckets = plan_buckets(l1, l2, ok_a[ia] & ok_b[ib], min_bucket)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for bk in buckets:
+            ids = bk.index
             if bk.kind == "batch":
-                f1, o1, l1, f2, o2, l2 = prepared
-                scores[bk.index] = api.score_batch_flat(f1, o1, l1, f2, o2, l2, params)
+                bl1, bl2 = l1[ids], l2[ids]
+                d_o1 = torch.from_numpy(o1[ids]).to(dev); d_o2 = torch.from_numpy(o2[ids]).to(dev)
+                d_l1 = torch.from_numpy(bl1).to(dev); d_l2 = torch.from_numpy(bl2).to(dev)
+                d_sc = torch.empty(len(ids), dtype=torch.int32, device=dev)
+                short, long_ = np.minimum(bl1, bl2), np.maximum(bl1, bl2)
+                cells = int((bl1.astype(np.int64) * bl2).sum())
+                pb = api.PackedBatch(ctx, fa.data_ptr(), d_o1.data_ptr(), d_l1.data_ptr(), fb.data_ptr(), d_o2.data_ptr(),
+                                     d_l2.data_ptr(), len(ids), int(short.max()), int(long_.max()), cells, stream=stream)
+                try:
+                    pb.score(d_sc.data_ptr(), params, stream=stream)
+                finally:
+                    pb.close()
+                scores[ids] = d_sc.cpu().numpy()
             else:
-                for pid in bk.index:
-                    scores[pid] = api.score(a.seq(int(ia[pid])), b.seq(int(ib[pid])), params)
+                for pid in ids:
+                    i1, i2 = int(ia[pid]), int(ib[pid])
+                    scores[pid] = ctx.score_device(fa.data_ptr() + int(a.offsets[i1]), int(a.lengths[i1]),
+                                                   fb.data_ptr() + int(b.offsets[i2]), int(b.lengths[i2]), params, stream=stream)
+    finally:
+        ctx.close()
     return scores
 
 
