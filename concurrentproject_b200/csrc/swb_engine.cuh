@@ -302,6 +302,9 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
                            out_tag | ((uint32_t)(((out_base + i0) >> 8) >> out_shift) & 0xFFu));
       }
       // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): wait for the producer
+      bool spec = false;
+      const uint2* spec_e = in;
+      const uint2* spec_b = in;
       {
         const int q = i0 + SLACK + lane;
         uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
@@ -311,7 +314,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
           const uint32_t got =
               wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
           if (need) v = got;
-          if (q + kChunk < LT) epref = ld_entry(in + ((j + kChunk) & in_mask));   // next chunk, speculative
+          spec = q + kChunk < LT;                                   // next chunk's entry: loaded speculatively,
+          spec_e = in + ((j + kChunk) & in_mask);                   // half a chunk from now (between the two step loops)
           if (RB) {
             // translate from the producer's base (published once per block) into ours
             const long long bj = j >> 8;
@@ -322,7 +326,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
               if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
               v = add16x2(v, pack2(diff));
             }
-            if (q + kChunk < LT) bpref = ld_entry(in_bases + (((j + kChunk) >> 8) & inb_mask));
+            spec_b = in_bases + (((j + kChunk) >> 8) & inb_mask);
           }
         }
         sm->inbox[q & (kInbox - 1)] = v;
@@ -346,8 +350,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
 
       uint32_t Tnext = tabp[0], xnext = inbp[0];       // loaded one step ahead of use
-#pragma unroll 4
-      for (int k = 0; k < kChunk; ++k) {
+      auto step = [&](const int k) {
         const uint32_t Tlo = Tnext;
         const uint32_t xin = xnext;
         Tnext = tabp[k + 1];
@@ -425,7 +428,16 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         Thi = Tlo;
         // slot = producer step (always in range); steps whose T position is outside [0,LT) are never read
         if (emit) st_entry(outp + k, xsend, otag);
-      }
+      };
+      // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
+      // the speculative boundary loads of the next chunk in between: the band above only has to be
+      // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
+#pragma unroll 4
+      for (int k = 0; k < kChunk / 2; ++k) step(k);
+      if (spec) epref = ld_entry(spec_e);
+      if (RB && spec) bpref = ld_entry(spec_b);
+#pragma unroll 4
+      for (int k = kChunk / 2; k < kChunk; ++k) step(k);
 #if SWB_DEVICE_CODE
       if (P.prof) {
         const long long tp2 = clock64();
