@@ -309,7 +309,7 @@ struct Plan {
 // (configs 1, 3: short-chain row loop) per_row = 12.5 / 8 / 12 / 15.3 / 10.2 / 14 cycles for s16 affine /
 // s16 linear / s32 / re-based affine / re-based linear / byte-compare s32; with two warps per scheduler
 // (config 2: fewest-instructions row loop) 14 / 10 / 12.5 / 15 / 11 / 14.5, times 1.5 per warp.  A band starts
-// `lag` steps after the band above it (lane skew + 64 steps of poll look-ahead + ~60 steps of L2 visibility);
+// `lag` steps after the band above it (lane skew + 48 steps of poll look-ahead + ~60 steps of L2 visibility);
 // the pair is done when the last band is.  The estimate only steers the choice of kernel, never the result.
 double estimate(long long LQ, long long LT, int mode, int R, int config, int sms, bool two_sided = false) {
   const int rpb = swb::rows_per_band(R, mode);
@@ -323,7 +323,7 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
-  const double lag = skew + 64 + 60;
+  const double lag = skew + 48 + 60;        // 32 steps of poll granularity + 16 of speculative look-ahead + visibility
   if (two_sided) {            // each half has half the bands and half the warps
     const long long NBh = (NB + 1) / 2, Wh = std::max<long long>(W / 2, 1);
     const long long b = NBh - 1, w = b % Wh, r = b / Wh;
