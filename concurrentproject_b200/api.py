@@ -98,6 +98,20 @@ def score_end(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS) 
     return out.value, ie.value, je.value
 
 
+def score_span(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS) -> Tuple[int, int, int, int, int]:
+    """(score, i_start, j_start, i_end, j_end), 1-based inclusive, i in seq2 and j in seq1: where the best local
+    alignment starts and ends (swb200_score_span: end cell by the tracking kernel, start cell by the anchored
+    recurrence over the reversed prefixes).  All zero for score 0."""
+    a, b = _u8(seq1), _u8(seq2)
+    out = C.c_int(0)
+    span = (C.c_longlong * 4)()
+    p = _params(params)
+    rc = _lib.load().swb200_score_span(_ptr(a), len(a), _ptr(b), len(b), C.byref(p), C.byref(out), span)
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_span")
+    return (out.value,) + tuple(int(x) for x in span)
+
+
 def last_run(ctx: Optional["Context"] = None) -> dict:
     info = RunInfo()
     rc = _lib.load().swb200_last_run(ctx.handle if ctx else None, C.byref(info))

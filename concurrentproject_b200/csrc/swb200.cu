@@ -158,6 +158,12 @@ __global__ void combine_two_sided_kernel(const uint2* __restrict__ f0, const uin
   if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(result, best);
 }
 
+// dst[k] = src[n-1-k]: the reversed prefixes for the anchored start-cell pass.
+__global__ void reverse_bytes_kernel(const uint8_t* __restrict__ src, long long n, uint8_t* __restrict__ dst) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    dst[k] = src[n - 1 - k];
+}
+
 // 256-bit presence map of the byte values in a buffer.
 __global__ void presence_kernel(const uint8_t* __restrict__ src, long long n, uint32_t* bitmap) {
   __shared__ uint32_t local[8];
@@ -195,6 +201,7 @@ struct swb200_ctx {
   uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
   unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
   int* d_cand = nullptr; size_t cand_cap = 0;     // end-cell tracking: {H, T position, Q row} per band
+  uint8_t* d_rev = nullptr; size_t rev_cap = 0;   // start-cell pass: the two reversed prefixes
   int* d_result = nullptr;        // [0] score [1] status, [2..9] presence bitmap
   uint8_t* d_lut = nullptr;       // 256 bytes
   int* h_result = nullptr;        // pinned
@@ -317,8 +324,8 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
   const int skew = swb::mode_is_s32(mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  static const double kPerRowShort[8] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0, 14.0, 16.0};
-  static const double kPerRowLong[8] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5, 14.5, 16.5};
+  static const double kPerRowShort[10] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0, 14.0, 16.0, 14.5, 16.5};
+  static const double kPerRowLong[10] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5, 14.5, 16.5, 15.0, 17.0};
   const double per_row = (config == 2 ? kPerRowLong : kPerRowShort)[mode];
   double cyc_step = per_row * R + 39.0;
   if (config == 2) cyc_step *= 1.5;
@@ -346,6 +353,8 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   if (lanes == 33) pl.mode = 5;          // 32-bit lanes, any byte alphabet
   if (lanes == 34) pl.mode = 6;          // 32-bit lanes + position of the maximum
   if (lanes == 35) pl.mode = 7;          // the same for any byte alphabet
+  if (lanes == 36) pl.mode = 8;          // anchored recurrence + position of the maximum (start-cell pass)
+  if (lanes == 37) pl.mode = 9;
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
@@ -376,6 +385,8 @@ const void* kernel_for(const Plan& pl) {
     case 4: return swb::engine_kernel_mode4(pl.R, pl.config);
     case 6: return swb::engine_kernel_mode6(pl.R, pl.config);
     case 7: return swb::engine_kernel_mode7(pl.R, pl.config);
+    case 8: return swb::engine_kernel_mode8(pl.R, pl.config);
+    case 9: return swb::engine_kernel_mode9(pl.R, pl.config);
     default: return swb::engine_kernel_mode5(pl.R, pl.config);
   }
 }
@@ -453,7 +464,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
   } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
   if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 4, false, s))) return rc;
-  const bool track = pl.mode == 6 || pl.mode == 7;
+  const bool track = pl.mode >= 6;
   if (track && (ring || !end3)) return fail(SWB200_ERR_ARG, "end-cell tracking runs on one GPU through swb200_score_end");
   if (track && (rc = grow(c->d_cand, c->cand_cap, 3 * (size_t)NB + 3, false, s))) return rc;
 
@@ -467,7 +478,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
-  const bool generic = pl.mode == 5 || pl.mode == 7;       // raw bytes straight from the caller's buffers, nothing to encode
+  const bool generic = pl.mode == 5 || pl.mode == 7 || pl.mode == 9;       // raw bytes straight from the caller's buffers, nothing to encode
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
   const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
   if (!generic) {
@@ -580,7 +591,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
 // score 0.  Runs the 32-bit tracking kernel with seq2 striped and seq1 streamed, whatever the options say.
 int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
                         const swb200_params* pp, const swb200_options* oo, cudaStream_t s, int* score_out,
-                        long long* end_out = nullptr) {
+                        long long* end_out = nullptr, bool anchored = false) {
   const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
   swb200_options o = oo ? *oo : swb200_options{};
   if (end_out) { o.orient = 2; o.lanes = 0; o.two_sided = -1; o.rebase = -1; if (o.rows > 16) o.rows = 16; }
@@ -605,7 +616,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
   const bool rb_ok = o.rebase >= 0 && o.lanes != 32 && rebase_is_safe(p, o.rows ? o.rows : 16);
   int lanes = o.lanes == 32 ? 32 : 16;
   if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 8LL * 32767)) lanes = 17;
-  if (end_out) lanes = 34;
+  if (end_out) lanes = anchored ? 36 : 34;
   int end3[3] = {0, 0, 0};
   // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
   // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
@@ -614,7 +625,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
     int score = 0, status = 0;
     if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status, nullptr, end_out ? end3 : nullptr))) return rc;
     if (status & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off timed out");
-    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33 && lanes != 35) {
+    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33 && lanes != 35 && lanes != 37) {
       if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
       // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
       SWB_CUDA(cudaMemsetAsync(c->d_result + 16, 0, 8 * sizeof(int), s));
@@ -633,7 +644,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
         }
       if (distinct > 4) {
         // the reference compares raw bytes (main.cpp:28-33): score such pairs with the byte-compare kernel
-        lanes = end_out ? 35 : 33;
+        lanes = end_out ? (anchored ? 37 : 35) : 33;
         continue;
       }
       SWB_CUDA(cudaMemcpyAsync(c->d_lut, table, 256, cudaMemcpyHostToDevice, s));
@@ -737,7 +748,7 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
-  cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);
   cudaFreeHost(c->h_result);
@@ -815,6 +826,62 @@ int swb200_score_end(const unsigned char* seq1, long long n, const unsigned char
   rc = score_device_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, nullptr, s, score_out, e);
   *i_end = e[0]; *j_end = e[1];
   return rc;
+}
+
+// Score, start cell and end cell.  Pass 1: end cell (tracking kernel).  Pass 2: the anchored recurrence over the
+// reversed prefixes seq1[0..j_end), seq2[0..i_end): its maximum equals the score and sits at the start cell.
+static int score_span_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
+                             const swb200_params* p, cudaStream_t s, int* score_out, long long* span4) {
+  span4[0] = span4[1] = span4[2] = span4[3] = 0;
+  long long e[2] = {0, 0};
+  int rc = score_device_locked(c, d_seq1, n, d_seq2, m, p, nullptr, s, score_out, e);
+  if (rc || *score_out <= 0) return rc;
+  const long long ie = e[0], je = e[1];
+  const size_t off2 = ((size_t)je + 255) & ~(size_t)255;
+  if ((rc = grow(c->d_rev, c->rev_cap, off2 + (size_t)ie + 256, false, s))) return rc;
+  const int b1 = (int)std::min<long long>((je + 255) / 256, 8LL * c->sms), b2 = (int)std::min<long long>((ie + 255) / 256, 8LL * c->sms);
+  reverse_bytes_kernel<<<b1, 256, 0, s>>>(d_seq1, je, c->d_rev);
+  reverse_bytes_kernel<<<b2, 256, 0, s>>>(d_seq2, ie, c->d_rev + off2);
+  SWB_CUDA(cudaGetLastError());
+  const swb200_run_info first = c->info;
+  int score2 = 0;
+  long long r[2] = {0, 0};
+  if ((rc = score_device_locked(c, c->d_rev, je, c->d_rev + off2, ie, p, nullptr, s, &score2, r, /*anchored=*/true))) return rc;
+  if (score2 != *score_out) return fail(SWB200_ERR_CUDA, "internal: anchored pass does not reproduce the score");
+  c->info.engine_launches += first.engine_launches; c->info.aux_launches += first.aux_launches + 2;
+  c->info.engine_ms += first.engine_ms; c->info.cells += first.cells;
+  span4[0] = ie - r[0] + 1; span4[1] = je - r[1] + 1; span4[2] = ie; span4[3] = je;
+  return SWB200_OK;
+}
+
+int swb200_score_span_device(swb200_ctx* c, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2,
+                             long long m, const swb200_params* p, void* stream, int* score_out, long long span_out[4]) {
+  if (!c || !span_out || !score_out) return fail(SWB200_ERR_ARG, "null context or output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  return score_span_locked(c, d_seq1, n, d_seq2, m, p, (cudaStream_t)stream, score_out, span_out);
+}
+
+int swb200_score_span(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                      const swb200_params* p, int* score_out, long long span_out[4]) {
+  if (n < 0 || m < 0 || !score_out || !span_out || (n > 0 && !seq1) || (m > 0 && !seq2))
+    return fail(SWB200_ERR_ARG, "bad sequence arguments");
+  span_out[0] = span_out[1] = span_out[2] = span_out[3] = 0;
+  if (n == 0 || m == 0) {
+    if (p) { int rc = check_params(*p); if (rc) return rc; }
+    *score_out = 0;
+    return SWB200_OK;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->own_stream;
+  const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
+  if ((rc = grow(c->d_ascii, c->ascii_cap, off2 + (size_t)m + 256, false, s))) return rc;
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
+  return score_span_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, s, score_out, span_out);
 }
 
 int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, int m, const swb200_params* p,

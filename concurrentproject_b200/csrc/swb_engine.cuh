@@ -474,7 +474,13 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 //  window the key belongs to is noted once per chunk, when the lane's best H has grown.  Per band the warp
 //  reduces (max H, min T position, min Q row) into P.cand; the host reduces the bands by the same rule.
 //  Needs H < 2^20 and R <= 16.
-template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = false>
+//  ANCH (with TRACK): the ANCHORED recurrence -- every alignment starts at cell (0,0), H is not clamped at 0, the
+//  borders carry the gap costs (row 0: H(0,j) = -(open + (j-1)*min(ext, open)), column 0 likewise, E/F = -inf
+//  there).  Run on the reversed prefixes that end at the best alignment's end cell, the position of the maximum
+//  is that alignment's START cell.  Only lane 0 of a band starts with the column-0 border in its registers; the
+//  other lanes start at -inf (they are still left of column 0) and build column 0 from the F values arriving from
+//  above, which is exactly the recurrence of that column.
+template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = false, bool ANCH = false>
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
@@ -483,6 +489,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
   const int src_lane = (lane + 31) & 31;
   const int nopen = -P.gap_init, next = -P.gap_ext;
   const int fnext = -(P.gap_ext < P.gap_init ? P.gap_ext : P.gap_init);   // F carried down inside a lane
+  constexpr int NEG = -(1 << 29);                                         // ANCH: "minus infinity" (no s32 overflow within 2^21 steps)
   const uint32_t padb = (uint32_t)(P.mismatch + P.gap_init) & 0xFFu;
   const uint32_t padw = GEN ? 0x200u : padb * 0x01010101u;       // GEN: 0x200 equals no byte and no pad row (0x100)
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
@@ -528,6 +535,21 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
     int up_prev = nopen, xsH = nopen, xsF = nopen, yoldH = nopen, yoldF = nopen;
+    if (ANCH) {
+      // column 0 of the anchored matrix: H(i,0) = -(open + (i-1)*gmin) for i >= 1, H(0,0) = 0, E = -inf
+      const long long i_first = band * (32LL * R) + 1;            // 1-based row of lane 0's first row
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        Ho[r] = lane == 0 ? (int)(nopen + (i_first + r - 1) * fnext) + nopen : NEG;
+        E[r] = NEG;
+      }
+      const int h_above = i_first == 1 ? 0 : (int)(nopen + (i_first - 2) * fnext);     // H(i_first - 1, 0)
+      up_prev = lane == 0 ? h_above + nopen : NEG;
+      xsH = lane == 0 ? Ho[R - 1] : NEG;
+      xsF = lane == 0 ? Ho[R - 1] - nopen : NEG;                  // F(i,0) = H(i,0) in column 0
+      yoldH = (lane == 0 && zero_src) ? nopen + nopen : NEG;      // band 0: H(0,1) - open; later bands: set by the wait below
+      yoldF = NEG;
+    }
     int bestkey = 0, rec_h = 0, rec_key = 0;         // TRACK only
     int rec_win = 0;
 
@@ -580,6 +602,10 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       {
         const int q = i0 + SLACK + lane;
         uint32_t vH = (uint32_t)nopen, vF = (uint32_t)nopen;
+        if (ANCH) {              // row 0 of the anchored matrix: H(0, q+1) - open, F = -inf (also beyond LT: harmless)
+          vH = (uint32_t)((int)(nopen + (long long)q * fnext) + nopen);
+          vF = (uint32_t)NEG;
+        }
         if (!zero_src) {
           const bool need = q < LT;
           const long long j = in_base + q + SKEW;
@@ -634,13 +660,13 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
             const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
             const int old = Ho[r];
             E[r] = addmax32(E[r], next, old);
-            const int m = addmaxrelu32(diag, s, E[r]);
+            const int m = ANCH ? addmax32(diag, s, E[r]) : addmaxrelu32(diag, s, E[r]);
             F = addmax32(F, r == 0 ? next : fnext, X);
             X = m + nopen;
             const int h = m > F ? m : F;
             Ho[r] = h + nopen;
             diag = old;
-            if (TRACK) { const int key = h * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
+            if (TRACK) { const int key = (ANCH ? (h > 0 ? h : 0) : h) * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
             else if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
           }
         } else {
@@ -652,11 +678,11 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
             const int old = Ho[r];
             E[r] = addmax32(E[r], next, old);
             F = addmax32(F, next, Hup);
-            const int h = max3relu32(d, E[r], F);
+            const int h = ANCH ? max3_32(d, E[r], F) : max3relu32(d, E[r], F);
             Ho[r] = h + nopen;
             Hup = Ho[r];
             diag = old;
-            if (TRACK) { const int key = h * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
+            if (TRACK) { const int key = (ANCH ? (h > 0 ? h : 0) : h) * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
             else if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
           }
         }
@@ -696,7 +722,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 
 // rows of Q one band covers
 // modes 2, 5, 6, 7 run 32-bit lanes (6, 7 = 2, 5 with end-cell tracking)
-SWB_HD bool mode_is_s32(int mode) { return mode == 2 || mode >= 5; }
+SWB_HD bool mode_is_s32(int mode) { return mode == 2 || mode >= 5; }      // 8, 9 = 6, 7 with the anchored recurrence
 SWB_HD int rows_per_band(int R, int mode) { return (mode_is_s32(mode) ? 32 : 64) * R; }
 
 }  // namespace swb

@@ -25,6 +25,8 @@ const void* engine_kernel_mode4(int R, int config);
 const void* engine_kernel_mode5(int R, int config);   // s32, any byte alphabet (compare instead of table look-up)
 const void* engine_kernel_mode6(int R, int config);   // mode 2 + position of the maximum (swb200_score_end)
 const void* engine_kernel_mode7(int R, int config);   // mode 5 + position of the maximum
+const void* engine_kernel_mode8(int R, int config);   // mode 6 with the anchored recurrence (start cell, swb200_score_span)
+const void* engine_kernel_mode9(int R, int config);   // mode 7 with the anchored recurrence
 
 // One launch can carry two independent sub-problems (two-sided sweep): warps [0, split) run `a`, the rest run `b`,
 // each as its own ring with its own buffers.  split == 0: everything runs `a`.
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   else if constexpr (MODE == 5) engine_warp_s32<R, SLACK, true, SHORT>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 6) engine_warp_s32<R, SLACK, false, SHORT, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 7) engine_warp_s32<R, SLACK, true, SHORT, true>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 8) engine_warp_s32<R, SLACK, false, SHORT, true, true>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 9) engine_warp_s32<R, SLACK, true, SHORT, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT>(P, w, lw, &sm[wi]);
   else engine_warp_s16<R, MODE, SLACK, false, SHORT>(P, w, lw, &sm[wi]);
 }

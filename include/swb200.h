@@ -90,6 +90,16 @@ SWB200_API int swb200_score_end_device(swb200_ctx* ctx, const unsigned char* d_s
                             const unsigned char* d_seq2, long long m, const swb200_params* p, void* stream,
                             int* score_out, long long* i_end, long long* j_end);
 
+/* Score, START cell and end cell: span_out = {i_start, j_start, i_end, j_end}, 1-based and inclusive (i in seq2, j in
+ * seq1); the end cell as in swb200_score_end, the start cell the one closest to it (largest j_start, then largest
+ * i_start) among the optimal alignments that end there.  Two passes: the tracking kernel, then the anchored
+ * recurrence over the reversed prefixes.  All zero when the score is 0.  Same limits as swb200_score_end. */
+SWB200_API int swb200_score_span(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                      const swb200_params* p, int* score_out, long long span_out[4]);
+SWB200_API int swb200_score_span_device(swb200_ctx* ctx, const unsigned char* d_seq1, long long n,
+                             const unsigned char* d_seq2, long long m, const swb200_params* p, void* stream,
+                             int* score_out, long long span_out[4]);
+
 /* What the last swb200_score*_ call on this context actually ran. */
 typedef struct {
   int lanes;            /* 16 or 32 */

@@ -109,6 +109,68 @@ int oracle_gotoh_end(const unsigned char* seq1, const unsigned char* seq2, int n
   return best;
 }
 
+/* Anchored variant of main.cpp:57-63 (every alignment starts at cell (0,0); no clamp at 0; the borders carry the
+ * gap costs as the recurrence itself generates them): score and position of the maximum, same tie rule.
+ * On the reversed prefixes ending at an alignment's end cell this finds the alignment's start. */
+int oracle_gotoh_anchored_end(const unsigned char* seq1, const unsigned char* seq2, int n, int m, const oracle_params* p,
+                              int* i_end, int* j_end) {
+  *i_end = 0; *j_end = 0;
+  if (n < 0 || m < 0) return -1;
+  const long long NEGINF = -(1LL << 40);
+  long long* Hrow = (long long*)calloc((size_t)n + 1, sizeof(long long));
+  long long* Frow = (long long*)calloc((size_t)n + 1, sizeof(long long));
+  if (!Hrow || !Frow) { free(Hrow); free(Frow); return -1; }
+  const int ge = p->gap_ext, gi = p->gap_init;
+  Hrow[0] = 0; Frow[0] = NEGINF;
+  { long long e = NEGINF; for (int j = 1; j <= n; ++j) { e = (e - ge > Hrow[j - 1] - gi) ? e - ge : Hrow[j - 1] - gi; Hrow[j] = e; Frow[j] = NEGINF; } }
+  long long best = 0; int bi = 0, bj = 0;
+  for (int i = 1; i <= m; ++i) {
+    const unsigned char b = seq2[i - 1];
+    long long hdiag = Hrow[0];
+    const long long f0 = (Frow[0] - ge > Hrow[0] - gi) ? Frow[0] - ge : Hrow[0] - gi;   /* column 0: only F */
+    Hrow[0] = f0; Frow[0] = f0;
+    long long e = NEGINF, hleft = Hrow[0];
+    for (int j = 1; j <= n; ++j) {
+      e = (e - ge > hleft - gi) ? e - ge : hleft - gi;
+      const long long f = (Frow[j] - ge > Hrow[j] - gi) ? Frow[j] - ge : Hrow[j] - gi;
+      long long h = hdiag + (seq1[j - 1] == b ? p->match : p->mismatch);
+      if (e > h) h = e;
+      if (f > h) h = f;
+      hdiag = Hrow[j];
+      Hrow[j] = h;
+      Frow[j] = f;
+      hleft = h;
+      if (h > best || (h == best && h > 0 && (j < bj || (j == bj && i < bi)))) { best = h; bi = i; bj = j; }
+    }
+  }
+  free(Hrow); free(Frow);
+  *i_end = bi; *j_end = bj;
+  return (int)best;
+}
+
+/* Score, end cell and start cell of the best local alignment: end cell by the rule of oracle_gotoh_end; start cell =
+ * the cell where the anchored pass over the reversed prefixes (seq1[0..j_end), seq2[0..i_end)) reaches the score
+ * first (same rule in reversed coordinates: the start closest to the end in seq1, then in seq2).  1-based,
+ * both inclusive; all zero for score 0. */
+int oracle_gotoh_span(const unsigned char* seq1, const unsigned char* seq2, int n, int m, const oracle_params* p,
+                      int* i_start, int* j_start, int* i_end, int* j_end) {
+  *i_start = *j_start = 0;
+  const int s = oracle_gotoh_end(seq1, seq2, n, m, p, i_end, j_end);
+  if (s <= 0) return s;
+  unsigned char* r1 = (unsigned char*)malloc((size_t)*j_end + 1);
+  unsigned char* r2 = (unsigned char*)malloc((size_t)*i_end + 1);
+  if (!r1 || !r2) { free(r1); free(r2); return -1; }
+  for (int k = 0; k < *j_end; ++k) r1[k] = seq1[*j_end - 1 - k];
+  for (int k = 0; k < *i_end; ++k) r2[k] = seq2[*i_end - 1 - k];
+  int ri = 0, rj = 0;
+  const int s2 = oracle_gotoh_anchored_end(r1, r2, *j_end, *i_end, p, &ri, &rj);
+  free(r1); free(r2);
+  if (s2 != s) return -2;                      /* cannot happen: the best alignment ends at (i_end, j_end) */
+  *i_start = *i_end - ri + 1;
+  *j_start = *j_end - rj + 1;
+  return s;
+}
+
 int oracle_gotoh_last_row(const unsigned char* seq1, const unsigned char* seq2, int n, int m,
                           const oracle_params* p, int* Hrow_out, int* Frow_out) {
   if (n < 0 || m < 0) return -1;

@@ -39,6 +39,7 @@ static void run_lane(const EngineParams* P, WarpShared* ws, int lane, int lw, Wa
   const bool sh = g_short < 0 ? SLACK == 1 : g_short != 0;
   if (MODE == 2) { if (sh) engine_warp_s32<R, SLACK, false, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false>(*P, w, lw, sm); }
   else if (MODE == 6) { if (sh) engine_warp_s32<R, SLACK, false, true, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false, true>(*P, w, lw, sm); }
+  else if (MODE == 8) { if (sh) engine_warp_s32<R, SLACK, false, true, true, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false, true, true>(*P, w, lw, sm); }
   else if (MODE >= 3) {
     if (sh) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true>(*P, w, lw, sm);
     else engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, false>(*P, w, lw, sm);
@@ -57,6 +58,7 @@ static lane_fn pick2(int mode, int slack) {
   if (mode == 3) return slack ? run_lane<R, 3, 1> : run_lane<R, 3, 0>;
   if (mode == 4) return slack ? run_lane<R, 4, 1> : run_lane<R, 4, 0>;
   if (mode == 6) return slack ? run_lane<R, 6, 1> : run_lane<R, 6, 0>;      // 32-bit lanes + end cell
+  if (mode == 8) return slack ? run_lane<R, 8, 1> : run_lane<R, 8, 0>;      // anchored recurrence + position of the maximum
   return slack ? run_lane<R, 2, 1> : run_lane<R, 2, 0>;
 }
 static lane_fn pick(int R, int mode, int slack) {
@@ -91,7 +93,7 @@ int main(int argc, char** argv) {
 
   const int rpb = rows_per_band(R, mode);
   const int NB = (int)((LQ + rpb - 1) / rpb);
-  const long long skew = (mode == 2 || mode == 6) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
+  const long long skew = (mode == 2 || mode == 6 || mode == 8) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
   const int align = mode >= 3 ? kRebaseBlock : kChunk;
   long long nsteps = ((LT + skew + align - 1) / align) * align;
   long long ext_len = 1; int ext_shift = 0;
@@ -134,7 +136,7 @@ int main(int argc, char** argv) {
         th.emplace_back(fn, &P[g], &ws[(size_t)g * W + w], l, w, &sm[(size_t)g * W + w]);
   for (auto& x : th) x.join();
   printf("score=%d status=%d bands=%d nsteps=%lld", result[0], result[1], NB, nsteps);
-  if (mode == 6) {   // the host's reduction: best H, then smallest T position, then smallest Q row
+  if (mode == 6 || mode == 8) {   // the host's reduction: best H, then smallest T position, then smallest Q row
     int h = 0, pp = 0x7fffffff, rr = 0x7fffffff;
     for (int b = 0; b < NB; ++b) {
       const int ch = cand[3 * b], cp = cand[3 * b + 1], cr = cand[3 * b + 2];

@@ -62,6 +62,10 @@ def oracle():
         lib.oracle_gotoh_last_row.restype = C.c_int
         lib.oracle_gotoh_end.argtypes = sig + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.oracle_gotoh_end.restype = C.c_int
+        lib.oracle_gotoh_anchored_end.argtypes = sig + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.oracle_gotoh_anchored_end.restype = C.c_int
+        lib.oracle_gotoh_span.argtypes = sig + [C.POINTER(C.c_int)] * 4
+        lib.oracle_gotoh_span.restype = C.c_int
         lib.oracle_gotoh_mt.argtypes = sig + [C.c_int]
         lib.oracle_gotoh_mt.restype = C.c_int
         lib.oracle_gotoh_banded.argtypes = sig[:4] + [C.c_int, C.c_int, C.POINTER(OracleParams), C.POINTER(C.c_int64)]
@@ -124,6 +128,24 @@ def gotoh_end(s1, s2, p=DEFAULT):
     ie, je = C.c_int(0), C.c_int(0)
     best = oracle().oracle_gotoh_end(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), C.byref(ie), C.byref(je))
     return best, ie.value, je.value
+
+
+def gotoh_anchored_end(s1, s2, p=DEFAULT):
+    """Anchored recurrence (alignments start at the origin): (max score, i, j) by the same tie rule."""
+    a, b = _u8(s1), _u8(s2)
+    pp = _params(p)
+    ie, je = C.c_int(0), C.c_int(0)
+    best = oracle().oracle_gotoh_anchored_end(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), C.byref(ie), C.byref(je))
+    return best, ie.value, je.value
+
+
+def gotoh_span(s1, s2, p=DEFAULT):
+    """(score, i_start, j_start, i_end, j_end), 1-based inclusive; i in seq2, j in seq1."""
+    a, b = _u8(s1), _u8(s2)
+    pp = _params(p)
+    v = [C.c_int(0) for _ in range(4)]
+    best = oracle().oracle_gotoh_span(_ptr(a), _ptr(b), len(a), len(b), C.byref(pp), *[C.byref(x) for x in v])
+    return (best,) + tuple(x.value for x in v)
 
 
 def gotoh_mt(s1, s2, p=DEFAULT, threads=0):

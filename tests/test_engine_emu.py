@@ -39,7 +39,7 @@ def emu():
         out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],
                              capture_output=True, text=True, timeout=900, check=True, env=env).stdout
         d = dict(kv.split("=") for kv in out.split())
-        if mode == 6:      # end-cell tracking: (score, status, 1-based row in Q, 1-based position in T)
+        if mode in (6, 8): # end-cell tracking: (score, status, 1-based row in Q, 1-based position in T)
             return int(d["score"]), int(d["status"]), int(d["endrow"]) + 1, int(d["endpos"]) + 1, int(d["endh"])
         if not final_row:
             return int(d["score"]), int(d["status"])
@@ -107,6 +107,22 @@ def test_end_cell_tracking(emu, slack):
         want, wi, wj = O.gotoh_end(t, q, p)                      # seq1 = T (columns j), seq2 = Q (rows i)
         score, status, row, pos, endh = emu(q, t, R, 6, slack, W, 1, p)
         assert (score, status, endh) == (want, 0, want)
+        assert (row, pos) == (wi, wj), (k, nq, nt, R, W, p)
+
+
+@pytest.mark.parametrize("slack", [0, 1])
+def test_anchored_recurrence_finds_the_start_cell(emu, slack):
+    """ANCH variant of the 32-bit engine: alignments start at the origin, no clamp at 0, gap-cost borders; the
+    maximum and its position against the oracle's anchored DP, over several bands and rounds."""
+    for k, (nq, nt, R, W, p) in enumerate([(150, 200, 1, 2, O.DEFAULT), (300, 260, 2, 3, (3, -2, 4, 1)), (200, 330, 1, 1, (2, -3, 1, 3)),
+                                           (260, 120, 4, 2, (1, -1, 0, 0))]):
+        core = rng.random_acgt(950 + k, 0, min(nq, nt) // 2)
+        q = np.concatenate([rng.mutate(core, 950 + k, 5, 0.06, 0.03), rng.random_acgt(950 + k, 1, nq)])[:nq]
+        t = np.concatenate([core, rng.random_acgt(950 + k, 2, nt)])[:nt]
+        want, wi, wj = O.gotoh_anchored_end(t, q, p)             # seq1 = T (columns j), seq2 = Q (rows i)
+        assert want > 0
+        score, status, row, pos, endh = emu(q, t, R, 8, slack, W, 1, p)
+        assert (status, endh) == (0, want), (k, p)
         assert (row, pos) == (wi, wj), (k, nq, nt, R, W, p)
 
 

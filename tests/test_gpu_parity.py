@@ -358,3 +358,33 @@ def test_score_end_reports_the_end_cell_of_the_best_alignment(api):
     assert api.score_end("GATTACA", "GCATGCU") == O.gotoh_end(b"GATTACA", b"GCATGCU")
     with pytest.raises(Exception):
         api.score_end(np.full(2_000_000, 65, np.uint8), np.full(2_000_000, 65, np.uint8))   # match*min(n,m) >= 2^20
+
+
+def test_score_span_reports_start_and_end_cell(api):
+    """Start cell by the anchored recurrence over the reversed prefixes (kernel modes 8/9) on top of the end cell:
+    against the oracle's span, plus two oracle-free properties -- the sub-rectangle the span cuts out scores the same,
+    and no smaller one does (dropping the first or the last row or column loses score)."""
+    r = np.random.default_rng(78)
+    for k, (n, m, p) in enumerate([(1500, 1500, O.DEFAULT), (6000, 900, (2, -3, 5, 1)), (800, 7000, (3, -2, 4, 1)),
+                                   (12000, 12000, O.DEFAULT), (2500, 2500, (2, -1, 1, 3)), (300, 200, (1, -1, 0, 0))]):
+        a = rng.random_acgt(700 + k, 0, n)
+        b = rng.random_acgt(700 + k, 1, m)
+        L = min(n, m) // 3
+        core = rng.mutate(a[n // 4: n // 4 + L], 700 + k, 9, 0.05, 0.02)
+        b = np.concatenate([b[: m // 3], core, b[m // 3 + len(core):]])[:m]
+        want = O.gotoh_span(a, b, p)
+        got = api.score_span(a, b, p)
+        assert got == want, (n, m, p, got, want)
+        s, i0, j0, i1, j1 = got
+        assert s == api.score(a, b, p) and 1 <= i0 <= i1 <= m and 1 <= j0 <= j1 <= n
+        sub = lambda di0, dj0, di1, dj1: O.gotoh_rolling(a[j0 - 1 + dj0: j1 - dj1], b[i0 - 1 + di0: i1 - di1], p)
+        assert sub(0, 0, 0, 0) == s
+        if p[0] > 0 and min(p[2], p[3]) > 0:
+            assert max(sub(1, 0, 0, 0), sub(0, 1, 0, 0)) <= s and sub(1, 1, 0, 0) < s      # the start cell is needed
+    a = rng.random_acgt(750, 0, 3000)
+    assert api.score_span(a, a) == (3000, 1, 1, 3000, 3000)
+    assert api.score_span(b"AAAA", b"CCCC") == (0, 0, 0, 0, 0)
+    x = r.integers(0, 20, 1200, dtype=np.uint8) + 65                                       # 20 symbols: byte-compare kernels
+    y = np.concatenate([r.integers(0, 20, 300, dtype=np.uint8) + 65, x[200:800], r.integers(0, 20, 100, dtype=np.uint8) + 65])
+    assert api.score_span(x, y) == O.gotoh_span(x, y)
+    assert api.score_span(x, y)[1:3] == (301, 201)
