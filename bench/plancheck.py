@@ -4,7 +4,7 @@ import sys, json, torch
 sys.path.insert(0, '.')
 from concurrentproject_b200 import api, rng
 ctx = api.Context(0)
-for n in (20000, 50000, 200000, 500000):
+for n in (20000, 50000, 100000, 200000, 500000):
     a = torch.from_numpy(rng.random_acgt(2, 0, n).copy()).cuda(); b = torch.from_numpy(rng.random_acgt(2, 1, n).copy()).cuda()
     def run(**kw):
         best = None

@@ -362,12 +362,15 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
       const int R = swb::kRowChoices[ri];
       if (o.rows && o.rows != R) continue;
       const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
-      if (e < best) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
+      if (e < best && !(o.two_sided > 0 && pl.two_sided)) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
       // two-sided: packed 16-bit lanes (plain or re-based), at least 4 bands per half
       if (allow_two_sided && (pl.mode <= 1 || pl.mode == 3 || pl.mode == 4) && o.two_sided >= 0 &&
           LQ >= 8LL * swb::rows_per_band(R, pl.mode)) {
         const double e2 = estimate(LQ, LT, pl.mode, R, ci, sms, true);
-        if (e2 < 0.97 * best || (o.two_sided > 0 && (e2 < best || !pl.two_sided))) { best = std::min(best, e2); pl.R = R; pl.config = ci; pl.two_sided = true; }
+        // a two-sided plan must beat a one-sided one by 3 % (it costs four more small launches); among two-sided plans
+        // the cheaper one wins
+        const bool better = pl.two_sided ? e2 < best : (e2 < 0.97 * best || o.two_sided > 0);
+        if (better) { best = std::min(best, e2); pl.R = R; pl.config = ci; pl.two_sided = true; }
       }
     }
   }
