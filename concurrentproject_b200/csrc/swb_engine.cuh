@@ -26,6 +26,11 @@
 
 namespace swb {
 
+// step-loop unroll factor: 8 measured 10 % faster than 4 on cfg2 (4.72 -> 4.28 ms); 16 and 2 are slower
+#ifndef SWB_STEP_UNROLL
+#define SWB_STEP_UNROLL 8
+#endif
+constexpr int kStepUnroll = SWB_STEP_UNROLL;
 constexpr int kChunk = 32;     // steps between boundary polls / table refills
 constexpr int kTabRing = 256;  // per-warp ring of substitution tables (one per T position), kept twice
 constexpr int kInbox = 64;     // per-warp ring of validated top-boundary values
@@ -442,11 +447,11 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
       // the speculative boundary loads of the next chunk in between: the band above only has to be
       // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
-#pragma unroll 4
+#pragma unroll (kStepUnroll)
       for (int k = 0; k < kChunk / 2; ++k) step(k);
       if (spec) epref = ld_entry(spec_e);
       if (RB && spec) bpref = ld_entry(spec_b);
-#pragma unroll 4
+#pragma unroll (kStepUnroll)
       for (int k = kChunk / 2; k < kChunk; ++k) step(k);
 #if SWB_DEVICE_CODE
       if (SWB_PROF) {
