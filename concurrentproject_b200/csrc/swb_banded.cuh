@@ -20,7 +20,11 @@
 #pragma once
 #include "swb_engine.cuh"
 
+#ifndef SWB_BANDED_UNROLL
+#define SWB_BANDED_UNROLL 4
+#endif
 namespace swb {
+constexpr int kSwbBandedUnroll = SWB_BANDED_UNROLL;   // step-loop unroll factor
 
 constexpr int kBandRing = 128;     // ring entries (tables per column / selectors per row), kept twice
 constexpr int kBandThreads = 16;   // threads per pair
@@ -117,7 +121,7 @@ SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_
       const uint32_t* selp = sel + ((Y0 + c * kChunk) & (kBandRing - 1));
       const uint32_t* tabp = tab + ((X0 + c * kChunk) & (kBandRing - 1));
       uint32_t a0 = tabp[0], b0 = tabp[16];
-#pragma unroll 4
+#pragma unroll (kSwbBandedUnroll)
       for (int h = 0; h < kChunk; ++h) {
         const uint32_t sv = selp[h];
         const uint32_t a1 = tabp[h + 1], b1 = tabp[h + 17];

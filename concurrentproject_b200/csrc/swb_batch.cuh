@@ -9,7 +9,11 @@
 #pragma once
 #include "swb_engine.cuh"
 
+#ifndef SWB_BATCH_UNROLL
+#define SWB_BATCH_UNROLL 4
+#endif
 namespace swb {
+constexpr int kSwbBatchUnroll = SWB_BATCH_UNROLL;   // step-loop unroll factor
 
 constexpr int kBatchRing = 128;   // per-group ring of substitution tables, kept twice
 
@@ -102,7 +106,7 @@ SWB_HD void batch_warp(const BatchParams& P, const WarpCtx& w, long long warp_id
       w.sync();
       const uint32_t* tabp = tab + ((i0 - SK * gl) & (kBatchRing - 1));
       uint32_t Tnext = tabp[0];
-#pragma unroll 4
+#pragma unroll (kSwbBatchUnroll)
       for (int k = 0; k < kChunk; ++k) {
         const uint32_t Tlo = Tnext;
         Tnext = tabp[k + 1];

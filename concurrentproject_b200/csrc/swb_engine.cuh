@@ -31,6 +31,10 @@ namespace swb {
 #define SWB_STEP_UNROLL 8
 #endif
 constexpr int kStepUnroll = SWB_STEP_UNROLL;
+#ifndef SWB_STEP_UNROLL32
+#define SWB_STEP_UNROLL32 4
+#endif
+constexpr int kStepUnroll32 = SWB_STEP_UNROLL32;   // 32-bit engine
 constexpr int kChunk = 32;     // steps between boundary polls / table refills
 constexpr int kTabRing = 256;  // per-warp ring of substitution tables (one per T position), kept twice
 constexpr int kInbox = 64;     // per-warp ring of validated top-boundary values
@@ -657,7 +661,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       uint32_t Tnext = tabp[0];
       int xnH = (int)inbp[0], xnF = (int)inbp[2 * kInbox];
       int cstep = ((127 - (int)(i0 & 127)) << 4) + 15;      // TRACK: low key bits of row 0 at the chunk's first step
-#pragma unroll 4
+#pragma unroll (kStepUnroll32)
       for (int k = 0; k < kChunk; ++k) {
         const uint32_t Tw = Tnext;
         const int xinH = xnH, xinF = xnF;
