@@ -32,7 +32,7 @@ namespace swb {
 #endif
 constexpr int kStepUnroll = SWB_STEP_UNROLL;
 #ifndef SWB_STEP_UNROLL32
-#define SWB_STEP_UNROLL32 4
+#define SWB_STEP_UNROLL32 8
 #endif
 constexpr int kStepUnroll32 = SWB_STEP_UNROLL32;   // 32-bit engine
 constexpr int kChunk = 32;     // steps between boundary polls / table refills
