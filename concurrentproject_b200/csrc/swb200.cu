@@ -312,8 +312,8 @@ struct Plan {
 };
 
 // Estimated cycles for one (R, config) choice.  Model and constants fitted to B200 sweeps
-// (profiles/r01_sweep_*.jsonl): a warp-step costs per_row*R + 39 cycles.  With one warp per scheduler
-// (configs 1, 3: short-chain row loop) per_row = 12.5 / 8 / 12 / 15.3 / 10.2 / 14 cycles for s16 affine /
+// (profiles/r01_sweep_*.jsonl): a warp-step costs per_row*R + 30 cycles (39 in config 2).  With one warp per scheduler
+// (configs 1, 3: short-chain row loop, step loops unrolled 8x) per_row = 13.2 / 7.5 / 12 / 15.6 / 9.8 / 14 cycles for s16 affine /
 // s16 linear / s32 / re-based affine / re-based linear / byte-compare s32; with two warps per scheduler
 // (config 2: fewest-instructions row loop) 14 / 10 / 12.5 / 15 / 11 / 14.5, times 1.5 per warp.  A band starts
 // `lag` steps after the band above it (lane skew + 48 steps of poll look-ahead + ~60 steps of L2 visibility);
@@ -324,10 +324,11 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
   const int skew = swb::mode_is_s32(mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  static const double kPerRowShort[10] = {12.5, 8.0, 12.0, 15.3, 10.2, 14.0, 14.0, 16.0, 14.5, 16.5};
+  static const double kPerRowShort[10] = {13.2, 7.5, 12.0, 15.6, 9.8, 14.0, 14.0, 16.0, 14.5, 16.5};
   static const double kPerRowLong[10] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5, 14.5, 16.5, 15.0, 17.0};
   const double per_row = (config == 2 ? kPerRowLong : kPerRowShort)[mode];
-  double cyc_step = per_row * R + 39.0;
+  double cyc_step = per_row * R + (config == 2 ? 39.0 : 30.0);
+  if (config != 2) cyc_step = std::max(cyc_step, 55.0);      // latency floor of a step with one warp per scheduler
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
   const double lag = skew + 48 + 60;        // 32 steps of poll granularity + 16 of speculative look-ahead + visibility

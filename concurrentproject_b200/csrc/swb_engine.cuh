@@ -26,11 +26,14 @@
 
 namespace swb {
 
-// step-loop unroll factor: 8 measured 10 % faster than 4 on cfg2 (4.72 -> 4.28 ms); 16 and 2 are slower
+// Step-loop unroll factor.  8 measured 10 % faster than 4 on cfg2 (4.72 -> 4.28 ms; 16 and 2 are slower) -- as long as
+// the unrolled loop stays below ~800 instructions: with 12 or more affine rows per lane it got 15-30 % SLOWER
+// (instruction cache), so the factor follows the size of one step.
 #ifndef SWB_STEP_UNROLL
 #define SWB_STEP_UNROLL 8
 #endif
 constexpr int kStepUnroll = SWB_STEP_UNROLL;
+SWB_HD constexpr int step_unroll(double instr_per_row, int rows, int big) { return instr_per_row * rows + 10.0 <= 100.0 ? big : 4; }
 #ifndef SWB_STEP_UNROLL32
 #define SWB_STEP_UNROLL32 8
 #endif
@@ -172,6 +175,7 @@ template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 2 + SLACK;        // T positions between neighbouring lanes
   constexpr int SKEW = 31 * SK + 1;    // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
+  constexpr int kU = step_unroll(MODE == 0 ? (RB ? 8.5 : 7.5) : (RB ? 5.5 : 4.5), R, kStepUnroll);
   const int lane = w.lane;
   const bool last_lane = lane == 31;
   const int src_lane = (lane + 31) & 31;
@@ -451,11 +455,11 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
       // the speculative boundary loads of the next chunk in between: the band above only has to be
       // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
-#pragma unroll (kStepUnroll)
+#pragma unroll (kU)
       for (int k = 0; k < kChunk / 2; ++k) step(k);
       if (spec) epref = ld_entry(spec_e);
       if (RB && spec) bpref = ld_entry(spec_b);
-#pragma unroll (kStepUnroll)
+#pragma unroll (kU)
       for (int k = kChunk / 2; k < kChunk; ++k) step(k);
 #if SWB_DEVICE_CODE
       if (SWB_PROF) {
@@ -506,6 +510,7 @@ template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = fa
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
+  constexpr int kU = step_unroll(8.0, R, kStepUnroll32);
   const int lane = w.lane;
   const bool last_lane = lane == 31;
   const int src_lane = (lane + 31) & 31;
@@ -661,7 +666,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
       uint32_t Tnext = tabp[0];
       int xnH = (int)inbp[0], xnF = (int)inbp[2 * kInbox];
       int cstep = ((127 - (int)(i0 & 127)) << 4) + 15;      // TRACK: low key bits of row 0 at the chunk's first step
-#pragma unroll (kStepUnroll32)
+#pragma unroll (kU)
       for (int k = 0; k < kChunk; ++k) {
         const uint32_t Tw = Tnext;
         const int xinH = xnH, xinF = xnF;
