@@ -388,3 +388,37 @@ def test_score_span_reports_start_and_end_cell(api):
     y = np.concatenate([r.integers(0, 20, 300, dtype=np.uint8) + 65, x[200:800], r.integers(0, 20, 100, dtype=np.uint8) + 65])
     assert api.score_span(x, y) == O.gotoh_span(x, y)
     assert api.score_span(x, y)[1:3] == (301, 201)
+
+
+def test_batch_properties_at_scale(api):
+    """cfg4- and cfg5-shaped batches too large for the oracle, through properties that need none: a read cut out of
+    its window scores its length; the score does not depend on the pair's place in the batch (shuffle) nor on the
+    argument order; a sample agrees with the single-pair engine; the banded kernel scores an identical pair its length."""
+    r = np.random.default_rng(99)
+    npairs, rl, wl = 120000, 150, 1000
+    wins = rng.random_acgt(990, 0, npairs * wl).reshape(npairs, wl)
+    offs = r.integers(0, wl - rl, size=npairs)
+    reads = np.stack([wins[k, o:o + rl] for k, o in enumerate(offs[:2000])])                 # exact substrings
+    reads = np.concatenate([reads, rng.random_acgt(990, 1, (npairs - 2000) * rl).reshape(-1, rl)])
+    f1, f2 = reads.reshape(-1).copy(), wins.reshape(-1).copy()
+    o1 = np.arange(npairs, dtype=np.int64) * rl; o2 = np.arange(npairs, dtype=np.int64) * wl
+    l1 = np.full(npairs, rl, np.int32); l2 = np.full(npairs, wl, np.int32)
+    got = api.score_batch_flat(f1, o1, l1, f2, o2, l2)
+    assert (got[:2000] == rl).all()
+    assert 15 < got[2000:].min() and got[2000:].max() < 70                                    # unrelated 150 x 1000 pairs
+    perm = r.permutation(npairs)
+    assert np.array_equal(api.score_batch_flat(f1, o1[perm], l1, f2, o2[perm], l2), got[perm])
+    assert np.array_equal(api.score_batch_flat(f2, o2, l2, f1, o1, l1), got)
+    for k in r.integers(0, npairs, size=25):
+        assert api.score(reads[k], wins[k]) == got[k]
+    assert np.array_equal(api.score_batch_flat(f1, o1, l1, f2, o2, l2, (2, -3, 5, 1), no_linear=True)[:2000], np.full(2000, 2 * rl))
+    # banded, cfg5 shape: 3000 pairs of 10 kb, identical / shifted by an insertion that stays inside the band
+    n, nb = 10000, 3000
+    a = rng.random_acgt(991, 0, nb * n).reshape(nb, n)
+    b = a.copy()
+    b[1::2, 5000:5010] = a[1::2, 5010:5020]                                                   # a few substitutions in every other pair
+    ob = np.arange(nb, dtype=np.int64) * n; lb = np.full(nb, n, np.int32)
+    sb = api.score_banded_batch_flat(a.reshape(-1), ob, lb, b.reshape(-1), ob, lb, -32, 31)
+    assert (sb[0::2] == n).all() and (sb[1::2] < n).all() and (sb[1::2] > n - 40).all()
+    for k in (1, 7, 2999):
+        assert sb[k] == O.gotoh_banded(a[k], b[k], -32, 31)
