@@ -165,7 +165,7 @@ def ncu_traffic(workload):
         return None
     try:
         d = json.load(open(ROOT / "profiles" / "r01_ncu_summary.json"))
-        return int(d["r01_cfg2_final4.ncu-rep"]["dram_bytes_per_launch"])
+        return int(d["r01_cfg2_final5.ncu-rep"]["dram_bytes_per_launch"])
     except Exception:
         return None
 
