@@ -122,3 +122,33 @@ def test_oracle_equals_live_reference_on_fresh_inputs():
         want = O.ref_call("ref_SmithWatermanScore", a, b)
         assert want == O.ref_call("ref_LazySmith", a, b) == O.ref_call("ref_ParallelLazySmith_threads", a, b)
         assert O.gotoh_rolling(a, b) == want and O.gotoh_full(a, b) == want and O.lazy_smith(a, b) == want
+
+
+def test_end_cell_and_span_oracles_are_self_consistent():
+    """oracle_gotoh_end / oracle_gotoh_span (new semantics, no reference counterpart): the score equals main.cpp's, the
+    end cell holds the maximum and is the first one in (j, i) order, the span's sub-rectangle scores the same and its
+    corner cells are aligned matches."""
+    r = np.random.default_rng(123)
+    for trial in range(60):
+        n, m = int(r.integers(1, 90)), int(r.integers(1, 90))
+        k = int(r.integers(2, 5))
+        a = r.integers(0, k, n, dtype=np.uint8) + 65
+        b = r.integers(0, k, m, dtype=np.uint8) + 65
+        p = [(1, -1, 1, 1), (2, -3, 5, 1), (3, -2, 2, 2), (2, -1, 1, 3), (1, -1, 0, 0), (4, -1, 2, 5)][trial % 6]
+        s = O.gotoh_full(a, b, p)
+        se, ie, je = O.gotoh_end(a, b, p)
+        assert se == s
+        sp = O.gotoh_span(a, b, p)
+        assert sp[0] == s and sp[3:] == (ie, je)
+        if s == 0:
+            assert sp == (0, 0, 0, 0, 0)
+            continue
+        i0, j0 = sp[1], sp[2]
+        assert 1 <= i0 <= ie <= m and 1 <= j0 <= je <= n
+        assert O.gotoh_full(a[j0 - 1:je], b[i0 - 1:ie], p) == s
+        assert a[je - 1] == b[ie - 1] and a[j0 - 1] == b[i0 - 1]          # a best alignment starts and ends on a match
+        # no cell with the maximum lies before the end cell in (j, i) order: prefixes that stop short of it score less
+        if je > 1:
+            assert O.gotoh_full(a[:je - 1], b, p) < s
+        if ie > 1:
+            assert O.gotoh_full(a[:je], b[:ie - 1], p) < s
