@@ -5,11 +5,12 @@ API fails loudly.  Nothing in this package computes a score on the CPU."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libswb200.so"
+LIB_PATH = Path(os.environ["SWB200_LIB"]) if os.environ.get("SWB200_LIB") else PKG / "lib" / "libswb200.so"   # SWB200_LIB: measurement builds (bench/knock.sh)
 
 
 class Params(C.Structure):
@@ -39,6 +40,10 @@ U8P = C.POINTER(C.c_ubyte)
 EXPORTS = {
     "swb200_last_error": ([], C.c_char_p),
     "swb200_device_count": ([], C.c_int),
+    "swb200_configure": ([C.c_char_p, C.c_char_p], C.c_int),
+    "swb200_set_devices": ([C.c_int], C.c_int),
+    "swb200_get_devices": ([], C.c_int),
+    "swb200_score_banded": ([U8P, C.c_int, U8P, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_int)], C.c_int),
     "swb200_score": ([U8P, C.c_int, U8P, C.c_int, C.POINTER(Params), C.POINTER(C.c_int)], C.c_int),
     "swb200_score_ex": ([U8P, C.c_longlong, U8P, C.c_longlong, C.POINTER(Params), C.POINTER(Options),
                          C.POINTER(C.c_int)], C.c_int),
@@ -69,6 +74,10 @@ EXPORTS = {
     "swb200_ring_create": ([C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p), C.c_char * 64], C.c_int),
     "swb200_ring_connect": ([C.c_void_p, C.c_char * 64], C.c_int),
     "swb200_ring_connect_local": ([C.c_void_p, C.c_void_p], C.c_int),
+    "swb200_ring_connect_root": ([C.c_void_p, C.c_char * 64], C.c_int),
+    "swb200_ring_connect_root_local": ([C.c_void_p, C.c_void_p], C.c_int),
+    "swb200_ring_combine_pending": ([C.c_void_p], C.c_int),
+    "swb200_ring_combine": ([C.c_void_p, C.c_void_p, C.POINTER(C.c_int)], C.c_int),
     "swb200_ring_score_device": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(Params),
                                   C.POINTER(Options), C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "swb200_ring_destroy": ([C.c_void_p], None),

@@ -112,6 +112,13 @@ def score_span(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS)
     return (out.value,) + tuple(int(x) for x in span)
 
 
+def configure(key: str, value) -> None:
+    """Debugging / measurement switches of the library (swb200_configure; include/swb200.h lists the keys)."""
+    rc = _lib.load().swb200_configure(key.encode(), str(value).encode())
+    if rc != 0:
+        raise SwbError(rc, "swb200_configure")
+
+
 def last_run(ctx: Optional["Context"] = None) -> dict:
     info = RunInfo()
     rc = _lib.load().swb200_last_run(ctx.handle if ctx else None, C.byref(info))

@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <climits>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -23,6 +25,38 @@
 namespace {
 
 thread_local std::string g_err;
+
+// Debugging / measurement switches.  Read from the environment ONCE (first use), changed afterwards only through
+// swb200_configure(); the scoring calls themselves never touch getenv.
+struct Settings {
+  long long spin_limit = 40LL * 1000 * 1000;   // SWB200_SPIN_LIMIT: polls before a waiting warp gives up
+  int dbg = 0;                                  // SWB200_DBG: timing experiments (1 = no boundary stores, 2 = no polls)
+  bool debug = false;                           // SWB200_DEBUG: print the post-mortem of a timed-out hand-off
+  std::string prof_path;                        // SWB200_PROF: per-warp cycle counters ("1" = stderr summary, else a file)
+  std::string dump_final_path;                  // SWB200_DUMP_FINAL: the two middle rows of a two-sided sweep
+  long long batch_chunk_bytes = 0;              // SWB200_BATCH_CHUNK_BYTES: tests force many small chunks
+  long long ring_min_cells = 200LL * 1000 * 1000 * 1000;   // SWB200_RING_MIN_CELLS: pairs at least this large use all devices
+};
+std::mutex g_settings_mu;
+Settings& settings_locked() {       // caller holds g_settings_mu
+  static Settings st;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("SWB200_SPIN_LIMIT")) st.spin_limit = atoll(e);
+    if (const char* e = getenv("SWB200_DBG")) st.dbg = atoi(e);
+    st.debug = getenv("SWB200_DEBUG") != nullptr;
+    if (const char* e = getenv("SWB200_PROF")) st.prof_path = e;
+    if (const char* e = getenv("SWB200_DUMP_FINAL")) st.dump_final_path = e;
+    if (const char* e = getenv("SWB200_BATCH_CHUNK_BYTES")) st.batch_chunk_bytes = std::max(1LL, atoll(e));
+    if (const char* e = getenv("SWB200_RING_MIN_CELLS")) st.ring_min_cells = std::max(1LL, atoll(e));
+  }
+  return st;
+}
+Settings settings() {               // a copy: cheap, and the caller needs no lock afterwards
+  std::lock_guard<std::mutex> lk(g_settings_mu);
+  return settings_locked();
+}
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -32,6 +66,16 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess)                                                                  \
       return fail(SWB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
   } while (0)
+
+// Every entry point switches to its context's device; the caller's current device is restored on every return path
+// (a host program or a torch process working on device A must not be left on device B).
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---------------------------------------------------------------------------------------------
 //  encode kernels: raw bytes -> 2-bit codes
@@ -207,6 +251,7 @@ struct swb200_ctx {
   int* h_result = nullptr;        // pinned
   unsigned epoch = 0;
   swb200_run_info info{};
+  long long* d_prof = nullptr; size_t prof_cap = 0;   // SWB200_PROF counters (grow-only, owned by the context)
   // grow-only staging of the host batch entry points (no cudaMalloc/cudaFree per call)
   uint8_t* hb_seq1 = nullptr; size_t hb_seq1_cap = 0;
   uint8_t* hb_seq2 = nullptr; size_t hb_seq2_cap = 0;
@@ -242,17 +287,36 @@ struct swb200_batch {
   long long cells = 0;
 };
 
+// What the root rank needs to combine the two halves of a two-sided sweep over the ring once every rank is done.
+struct RingCombine {
+  bool pending = false;
+  long long LT = 0, ext_len = 0, NB0 = 0, NB1 = 0;
+  int skew = 0, linear = 0, rebased = 0, gap_init = 0, gap_ext = 0;
+};
+
+// One rank's region: [0, 2*len) boundary stream of the forward ring (entries + bases), [2*len, 4*len) the same for the
+// reversed ring of a two-sided sweep, [4*len, 6*len) / [6*len, 8*len) the two middle boundary rows (only the ROOT
+// rank's copy is written: the ranks that own the two last bands store there through NVLink).
 struct swb200_ring {
   swb200_ctx* ctx = nullptr;
   int rank = 0, world = 1;
   uint2* inbound = nullptr;
-  size_t entries = 0;
+  size_t len = 0;              // entries per half-region unit (a power of two)
+  size_t entries = 0;          // 8 * len
   uint2* next = nullptr;
   bool next_is_ipc = false;
+  uint2* root = nullptr;       // rank 0's region (== inbound on rank 0); null: two-sided sweeps are off for this ring
+  bool root_is_ipc = false;
   unsigned calls = 0;
+  RingCombine combine;
 };
 
 namespace {
+
+// owners for objects under construction: an early SWB_CUDA return frees everything allocated so far
+struct CtxDeleter { void operator()(swb200_ctx* c) const { swb200_ctx_destroy(c); } };
+struct RingDeleter { void operator()(swb200_ring* r) const { swb200_ring_destroy(r); } };
+struct BatchDeleter { void operator()(swb200_batch* b) const { swb200_batch_free(b); } };
 
 template <typename T>
 int grow(T*& p, size_t& cap, size_t need, bool zero, cudaStream_t s) {
@@ -343,6 +407,10 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   return (start + (double)(LT + skew)) * cyc_step;
 }
 
+struct Plan;
+const void* kernel_for(const Plan& pl);
+constexpr int kAutoConfigs = 3;      // launch configs the planner chooses from by itself
+
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms,
                bool allow_two_sided = false) {
   Plan pl{};
@@ -358,10 +426,11 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   if (lanes == 37) pl.mode = 9;
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
-    if (o.config && o.config != ci) continue;
+    if (o.config ? o.config != ci : ci > kAutoConfigs) continue;       // the rest: only when asked for
     for (int ri = 0; ri < swb::kNumRowChoices; ++ri) {
       const int R = swb::kRowChoices[ri];
       if (o.rows && o.rows != R) continue;
+      { Plan probe = pl; probe.R = R; probe.config = ci; if (!kernel_for(probe)) continue; }
       const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
       if (e < best && !(o.two_sided > 0 && pl.two_sided)) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
       // two-sided: packed 16-bit lanes (plain or re-based), at least 4 bands per half
@@ -400,10 +469,12 @@ int log2_ceil(long long v) { int s = 0; while ((1LL << s) < v) ++s; return s; }
 // Present when the pair is spread over a ring of GPUs (one swb200_ring per rank).
 struct RingCfg {
   int rank, world;
-  uint2* inbound;        // this rank's boundary stream buffer (consumed by local warp 0)
-  uint2* next_inbound;   // the next rank's buffer, mapped into this process (peer stores over NVLink)
-  size_t inbound_entries;
+  uint2* inbound;        // this rank's region (consumed by local warp 0 of each half)
+  uint2* next_inbound;   // the next rank's region, mapped into this process (peer stores over NVLink)
+  size_t len;            // region unit (see swb200_ring)
   unsigned call_epoch;   // 1..16383, identical on all ranks for one collective call
+  uint2* root;           // rank 0's region, or null (then the plan is one-sided)
+  RingCombine* combine;  // filled in when the run was two-sided: the root combines after every rank has finished
 };
 
 // Encode + one engine run at a fixed lane width.  d_seq1/d_seq2 are device pointers.
@@ -411,7 +482,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
              const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
              int* score, int* status, const RingCfg* ring = nullptr, int* end3 = nullptr) {
   const int world = ring ? ring->world : 1;
-  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr);
+  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr || ring->root != nullptr);
   const void* kern = kernel_for(pl);
   if (!kern) return fail(SWB200_ERR_ARG, "no kernel for rows=" + std::to_string(pl.R));
   const uint8_t* dq = pl.swap ? d_seq2 : d_seq1;
@@ -458,13 +529,13 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   if (ts) {
     if ((rc = grow(c->d_q2, c->q2_cap, (size_t)(NB1 * rpb) + 64, false, s))) return rc;
     if ((rc = grow(c->d_t2, c->t2_cap, (size_t)(LT / 32 + 8), false, s))) return rc;
-    if ((rc = grow(c->d_final, c->final_cap, 4 * (size_t)ext_len, false, s))) return rc;
+    if (!ring && (rc = grow(c->d_final, c->final_cap, 4 * (size_t)ext_len, false, s))) return rc;
   }
   const size_t links_need = (size_t)std::max(warps, 1) * 2 * (size_t)link_len;
   const size_t ext_need = (ts ? 4 : 2) * (size_t)ext_len;
   if ((rc = grow(c->d_links, c->links_cap, links_need, true, s))) return rc;
   if (ring) {
-    if (2 * (size_t)ext_len > ring->inbound_entries)
+    if ((size_t)ext_len > ring->len)
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
   } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
   if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 4, false, s))) return rc;
@@ -503,7 +574,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   swb::EngineParams& P = L.a;
   P.q_codes = generic ? dq : c->d_q; P.t_packed = c->d_t; P.t_bytes = dt; P.LQ = ts ? mid : LQ; P.LT = LT; P.NB = (int)NB0;
   const int warps0 = ts ? split : warps;
-  P.ring_total = warps0 * world; P.ring_offset = ring ? ring->rank * warps : 0; P.warps_local = warps0;
+  P.ring_total = warps0 * world; P.ring_offset = ring ? ring->rank * warps0 : 0; P.warps_local = warps0;
   P.links = c->d_links; P.link_mask = (unsigned)(link_len - 1); P.link_shift = link_shift;
   P.progress = c->d_progress;
   P.ext_in = ring ? ring->inbound : c->d_ext; P.ext_out = ring ? ring->next_inbound : c->d_ext;
@@ -511,37 +582,47 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   P.tag_base = c->epoch << 26; P.result = c->d_result;
   P.ext_tag_base = ring ? (((ring->call_epoch >> 8) & 0x3Fu) << 26) | (ring->call_epoch & 0xFFu) : P.tag_base;
   P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
-  P.spin_limit = getenv("SWB200_SPIN_LIMIT") ? atoll(getenv("SWB200_SPIN_LIMIT")) : 40LL * 1000 * 1000;
-  P.dbg = getenv("SWB200_DBG") ? atoi(getenv("SWB200_DBG")) : 0;
+  const Settings cfg = settings();
+  P.spin_limit = cfg.spin_limit;
+  P.dbg = cfg.dbg;
   long long* d_prof = nullptr;
-  if (getenv("SWB200_PROF")) {
-    SWB_CUDA(cudaMalloc(&d_prof, (size_t)warps * 4 * sizeof(long long)));
-    SWB_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)warps * 4 * sizeof(long long), s));
+  if (!cfg.prof_path.empty()) {           // context-owned, grow-only: nothing to leak on an early return
+    if ((rc = grow(c->d_prof, c->prof_cap, (size_t)warps * 8, false, s))) return rc;
+    d_prof = c->d_prof;
+    SWB_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)warps * 8 * sizeof(long long), s));
   }
   P.prof = d_prof;
   P.cand = track ? c->d_cand : nullptr;
   L.split = split;
+  // the two middle boundary rows of a two-sided sweep: local buffer, or the root rank's region on a ring
+  uint2* final_f = ring ? ring->root + 4 * ring->len : c->d_final;
+  uint2* final_b = ring ? ring->root + 6 * ring->len : c->d_final + 2 * (size_t)ext_len;
   if (ts) {
-    P.final_out = c->d_final; P.final_mask = (unsigned)(ext_len - 1);
+    P.final_out = final_f; P.final_mask = (unsigned)(ext_len - 1);
     swb::EngineParams& B = L.b;
     B = P;
     B.q_codes = c->d_q2; B.t_packed = c->d_t2; B.LQ = NB1 * rpb; B.NB = (int)NB1;
-    B.warps_local = warps - split; B.ring_total = warps - split; B.ring_offset = 0;
+    B.warps_local = warps - split; B.ring_total = (warps - split) * world; B.ring_offset = ring ? ring->rank * (warps - split) : 0;
     B.links = c->d_links + (size_t)split * ring_stride;
     B.progress = c->d_progress + split + 2;
-    B.ext_in = c->d_ext + 2 * (size_t)ext_len; B.ext_out = c->d_ext + 2 * (size_t)ext_len;
-    B.final_out = c->d_final + 2 * (size_t)ext_len;
-    B.prof = d_prof ? d_prof + 4 * (size_t)split : nullptr;
+    B.ext_in = ring ? ring->inbound + 2 * ring->len : c->d_ext + 2 * (size_t)ext_len;
+    B.ext_out = ring ? ring->next_inbound + 2 * ring->len : c->d_ext + 2 * (size_t)ext_len;
+    B.final_out = final_b;
+    B.prof = d_prof ? d_prof + 8 * (size_t)split : nullptr;
   }
   void* args[] = {&L};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
-  if (ts) {
+  if (ts && ring) {
+    // the two last bands may live on any rank: the root combines once EVERY rank's kernel has finished
+    *ring->combine = RingCombine{true, LT, ext_len, NB0, NB1, skew, pl.mode == 1 || pl.mode == 4, pl.mode == 3 || pl.mode == 4,
+                                 p.gap_init, p.gap_ext};
+  } else if (ts) {
     // re-based lanes: the final bands' bases sit in the second half of each buffer, region (band & 3) of four
     const bool rb = pl.mode == 3 || pl.mode == 4;
-    const uint2* bf = rb ? c->d_final + (size_t)ext_len + (size_t)((NB0 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
-    const uint2* bb = rb ? c->d_final + 3 * (size_t)ext_len + (size_t)((NB1 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
-    combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(c->d_final, c->d_final + 2 * (size_t)ext_len, LT, skew,
+    const uint2* bf = rb ? final_f + (size_t)ext_len + (size_t)((NB0 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
+    const uint2* bb = rb ? final_b + (size_t)ext_len + (size_t)((NB1 - 1) & 3) * (size_t)(ext_len / 4) : nullptr;
+    combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(final_f, final_b, LT, skew,
                                                         pl.mode == 1 || pl.mode == 4, p.gap_init, p.gap_ext, bf, bb, c->d_result);
     c->info.aux_launches += 1;
   }
@@ -558,25 +639,35 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   *score = c->h_result[0];
   *status = c->h_result[1];
-  if (ts && getenv("SWB200_DUMP_FINAL")) {          // debugging aid: the two middle boundary rows as the kernels wrote them
+  if (ts && !ring && !cfg.dump_final_path.empty()) {          // debugging aid: the two middle boundary rows as the kernels wrote them
     std::vector<uint2> h(4 * (size_t)ext_len);
     cudaMemcpy(h.data(), c->d_final, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
-    FILE* f = fopen(getenv("SWB200_DUMP_FINAL"), "wb");
+    FILE* f = fopen(cfg.dump_final_path.c_str(), "wb");
     if (f) {
       long long hdr[6] = {LT, skew, ext_len, mid, pad1, (long long)pl.swap};
       fwrite(hdr, sizeof hdr, 1, f); fwrite(h.data(), sizeof(uint2), h.size(), f); fclose(f);
     }
   }
   if (d_prof) {
-    std::vector<long long> hp((size_t)warps * 4);
+    std::vector<long long> hp((size_t)warps * 8);
     cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(d_prof);
-    for (int wv = 0; wv < warps && wv < 12; ++wv)
-      fprintf(stderr, "prof warp %d: prologue %.0f cyc/chunk, steps %.0f cyc/chunk, failed polls %.2f/chunk, chunks %lld\n", wv,
-              hp[4 * wv + 3] ? (double)hp[4 * wv] / hp[4 * wv + 3] : 0.0, hp[4 * wv + 3] ? (double)hp[4 * wv + 1] / hp[4 * wv + 3] : 0.0,
-              hp[4 * wv + 3] ? (double)hp[4 * wv + 2] / hp[4 * wv + 3] : 0.0, hp[4 * wv + 3]);
+    if (cfg.prof_path == "1") {
+      for (int wv = 0; wv < warps && wv < 12; ++wv)
+        fprintf(stderr, "prof warp %d: prologue %.0f cyc/chunk, steps %.0f cyc/chunk, failed polls %.2f/chunk, chunks %lld\n", wv,
+                hp[8 * wv + 3] ? (double)hp[8 * wv] / hp[8 * wv + 3] : 0.0, hp[8 * wv + 3] ? (double)hp[8 * wv + 1] / hp[8 * wv + 3] : 0.0,
+                hp[8 * wv + 3] ? (double)hp[8 * wv + 2] / hp[8 * wv + 3] : 0.0, hp[8 * wv + 3]);
+    } else if (FILE* f = fopen(cfg.prof_path.c_str(), "a")) {
+      // one JSON line per launch: per warp [prologue cycles, step cycles, failed polls, chunks, t_start ns, t_end ns, SM]
+      fprintf(f, "{\"mode\": %d, \"R\": %d, \"config\": %d, \"ctas\": %lld, \"NB\": %lld, \"LT\": %lld, \"two_sided\": %d, \"split\": %d, \"ms\": %.4f, \"warps\": [",
+              pl.mode, pl.R, pl.config, ctas, NB, LT, (int)ts, split, ms);
+      for (int wv = 0; wv < warps; ++wv)
+        fprintf(f, "%s[%lld,%lld,%lld,%lld,%lld,%lld,%lld]", wv ? "," : "", hp[8 * wv], hp[8 * wv + 1], hp[8 * wv + 2], hp[8 * wv + 3],
+                hp[8 * wv + 4], hp[8 * wv + 5], hp[8 * wv + 6]);
+      fprintf(f, "]}\n");
+      fclose(f);
+    }
   }
-  if ((*status & swb::STATUS_SPIN_TIMEOUT) && getenv("SWB200_DEBUG"))
+  if ((*status & swb::STATUS_SPIN_TIMEOUT) && cfg.debug)
     fprintf(stderr, "libswb200: timeout kind=%d a=%d(0x%x) b=%d(0x%x) c=%d d=%d thread=%d  [mode=%d R=%d config=%d ctas=%lld NB=%lld LT=%lld link_len=%lld ext_len=%lld epoch=%u ts=%d]\n",
             c->h_result[3], c->h_result[4], c->h_result[4], c->h_result[5], c->h_result[5], c->h_result[6], c->h_result[7],
             c->h_result[8], pl.mode, pl.R, pl.config, ctas, NB, LT, link_len, ext_len, c->epoch, (int)ts);
@@ -609,6 +700,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
   if (n == 0 || m == 0) { *score_out = 0; return SWB200_OK; }   // both reference oracles return 0 here
   if (end_out && ((long long)p.match * std::min(n, m) >= (1LL << 20) || std::max(n, m) >= (1LL << 30)))
     return fail(SWB200_ERR_RANGE, "end-cell tracking needs match*min(n,m) < 2^20");
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
 
   const uint8_t* lut = nullptr;
@@ -705,12 +797,38 @@ int legacy(const unsigned char* a, const unsigned char* b, int n, int m, const c
 
 }  // namespace
 
+static bool pool_last_run(swb200_run_info* info);
+// host pair call: 1 = not a case for the device pool (score it on one GPU), otherwise the call's return code
+static int score_pair_on_pool(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                              const swb200_params* p, const swb200_options* opt, int* score_out);
+// host batch calls: one GPU, or contiguous ranges of pairs over the devices chosen with swb200_set_devices
+static int score_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                            const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                            const swb200_params* p, const swb200_options* opt, int banded, int band_lo, int band_hi,
+                            int* scores_out);
+
 // ---------------------------------------------------------------------------------------------
 //  exported C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
 const char* swb200_last_error(void) { return g_err.c_str(); }
+
+int swb200_configure(const char* key, const char* value) {
+  if (!key || !value) return fail(SWB200_ERR_ARG, "null key or value");
+  std::lock_guard<std::mutex> lk(g_settings_mu);
+  Settings& st = settings_locked();
+  const std::string k = key;
+  if (k == "spin_limit") st.spin_limit = atoll(value);
+  else if (k == "dbg") st.dbg = atoi(value);
+  else if (k == "debug") st.debug = atoi(value) != 0;
+  else if (k == "prof") st.prof_path = value;
+  else if (k == "dump_final") st.dump_final_path = value;
+  else if (k == "batch_chunk_bytes") st.batch_chunk_bytes = std::max(0LL, atoll(value));
+  else if (k == "ring_min_cells") st.ring_min_cells = std::max(1LL, atoll(value));
+  else return fail(SWB200_ERR_ARG, "unknown setting: " + k);
+  return SWB200_OK;
+}
 
 int swb200_device_count(void) {
   int n = 0;
@@ -726,6 +844,7 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
   if (e != cudaSuccess || count == 0)
     return fail(SWB200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
   if (device < 0 || device >= count) return fail(SWB200_ERR_ARG, "device index out of range");
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   SWB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -734,7 +853,7 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
   int coop = 0;
   SWB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   if (!coop) return fail(SWB200_ERR_CUDA, "device lacks cooperative launch");
-  swb200_ctx* c = new swb200_ctx();
+  std::unique_ptr<swb200_ctx, CtxDeleter> c(new swb200_ctx());
   c->device = device;
   c->sms = prop.multiProcessorCount;
   SWB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -744,18 +863,19 @@ int swb200_ctx_create(int device, swb200_ctx** ctx_out) {
   SWB_CUDA(cudaMalloc(&c->d_result, 32 * sizeof(int)));
   SWB_CUDA(cudaMalloc(&c->d_lut, 256));
   SWB_CUDA(cudaMallocHost(&c->h_result, 32 * sizeof(int)));
-  *ctx_out = c;
+  *ctx_out = c.release();
   return SWB200_OK;
 }
 
 void swb200_ctx_destroy(swb200_ctx* c) {
   if (!c) return;
+  DeviceGuard guard;
   cudaSetDevice(c->device);
   cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
-  cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFree(c->d_prof); cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);
-  cudaFreeHost(c->h_result);
+  if (c->h_result) cudaFreeHost(c->h_result);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -781,10 +901,12 @@ int swb200_score_ex(const unsigned char* seq1, long long n, const unsigned char*
     *score_out = 0;
     return SWB200_OK;
   }
+  if (const int prc = score_pair_on_pool(seq1, n, seq2, m, p, opt, score_out); prc != 1) return prc;
   swb200_ctx* c = nullptr;
   int rc = default_ctx(&c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = c->own_stream;
   // both sequences into one staging buffer, 256-byte aligned so the encoders can use 128-bit reads
@@ -820,6 +942,7 @@ int swb200_score_end(const unsigned char* seq1, long long n, const unsigned char
   int rc = default_ctx(&c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = c->own_stream;
   const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
@@ -879,6 +1002,7 @@ int swb200_score_span(const unsigned char* seq1, long long n, const unsigned cha
   int rc = default_ctx(&c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = c->own_stream;
   const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
@@ -896,6 +1020,7 @@ int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, in
 int swb200_last_run(swb200_ctx* c, swb200_run_info* info) {
   if (!info) return fail(SWB200_ERR_ARG, "null info");
   if (!c) {
+    if (pool_last_run(info)) return SWB200_OK;       // the last host-buffer call ran on the device pool
     int rc = default_ctx(&c);
     if (rc) return rc;
   }
@@ -924,9 +1049,10 @@ static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const lon
   if (!c || !out || npairs < 0 || max_short < 0 || max_long < 0 || (!keep_order && max_long < max_short))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
-  swb200_batch* b = new swb200_batch();
+  std::unique_ptr<swb200_batch, BatchDeleter> b(new swb200_batch());   // freed on every early return
   b->ctx = c; b->npairs = npairs; b->max_short = max_short; b->max_long = max_long; b->cells = total_cells;
   b->keep_order = keep_order ? 1 : 0;
   b->q_stride = std::max(1, (max_short + 31) / 32) + (keep_order ? 2 : 0);
@@ -936,7 +1062,7 @@ static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const lon
   if (pooled) {
     int rc;
     if ((rc = grow(c->hb_qw, c->hb_qw_cap, np * b->q_stride, false, s)) || (rc = grow(c->hb_tw, c->hb_tw_cap, np * b->t_stride, false, s)) ||
-        (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, s)) || (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, s))) { delete b; return rc; }
+        (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, s)) || (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, s))) return rc;
     b->q_words = c->hb_qw; b->t_words = c->hb_tw; b->q_len = c->hb_ql; b->t_len = c->hb_tl;
   } else {
     SWB_CUDA(cudaMalloc(&b->q_words, np * b->q_stride * sizeof(uint64_t)));
@@ -954,11 +1080,9 @@ static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const lon
   }
   SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   SWB_CUDA(cudaStreamSynchronize(s));
-  if (c->h_result[1] & swb::STATUS_BAD_SYMBOL) {
-    swb200_batch_free(b);
+  if (c->h_result[1] & swb::STATUS_BAD_SYMBOL)
     return fail(SWB200_ERR_ALPHABET, "batch input contains bytes other than A,C,G,T");
-  }
-  *out = b;
+  *out = b.release();
   return SWB200_OK;
 }
 
@@ -1056,6 +1180,7 @@ int swb200_batch_score(swb200_batch* b, const swb200_params* pp, const swb200_op
   if ((rc = check_params(p))) return rc;
   const BatchView v = whole_batch(b);
   if ((rc = check_batch_score(v, p, b->keep_order))) return rc;
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   c->info = swb200_run_info{};
@@ -1082,6 +1207,7 @@ int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const s
   if ((rc = check_params(p))) return rc;
   const BatchView v = whole_batch(b);
   if ((rc = check_banded_score(v, p, b->keep_order, band_lo, band_hi))) return rc;
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   c->info = swb200_run_info{};
@@ -1099,27 +1225,30 @@ int swb200_batch_score_banded(swb200_batch* b, int band_lo, int band_hi, const s
 
 void swb200_batch_free(swb200_batch* b) {
   if (!b) return;
+  DeviceGuard guard;
   cudaSetDevice(b->ctx->device);
   if (!b->pooled) { cudaFree(b->q_words); cudaFree(b->t_words); cudaFree(b->q_len); cudaFree(b->t_len); }
   delete b;
 }
 
-static int score_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
-                            const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
-                            const swb200_params* p, const swb200_options* opt, int banded, int band_lo, int band_hi,
-                            int* scores_out) {
+// One context's share of a host batch call (the whole batch on one GPU; a contiguous range of pairs when the batch is
+// sharded over several GPUs: off1/len1/... then point at the range's first pair, offsets stay absolute).
+static int score_batch_host_ctx(swb200_ctx* c, const unsigned char* seq1_all, const long long* off1, const int* len1,
+                                const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                                const swb200_params* p, const swb200_options* opt, int banded, int band_lo, int band_hi,
+                                int* scores_out) {
   if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !scores_out)))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   if (npairs == 0) return SWB200_OK;
-  swb200_ctx* c = nullptr;
-  int rc = default_ctx(&c);
-  if (rc) return rc;
-  long long bytes1 = 0, bytes2 = 0, cells = 0;
+  int rc;
+  long long bytes1 = 0, bytes2 = 0, cells = 0, base1 = LLONG_MAX, base2 = LLONG_MAX;
   int max_short = 0, max_long = 0;
   for (long long k = 0; k < npairs; ++k) {
     if (len1[k] < 0 || len2[k] < 0 || off1[k] < 0 || off2[k] < 0) return fail(SWB200_ERR_ARG, "negative length or offset");
     bytes1 = std::max(bytes1, off1[k] + len1[k]);
     bytes2 = std::max(bytes2, off2[k] + len2[k]);
+    base1 = std::min(base1, off1[k]);
+    base2 = std::min(base2, off2[k]);
     if (banded) { max_short = std::max(max_short, len1[k]); max_long = std::max(max_long, len2[k]); }
     else {
       max_short = std::max(max_short, std::min(len1[k], len2[k]));
@@ -1127,13 +1256,16 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
     }
     cells += (long long)len1[k] * len2[k];
   }
+  base1 &= ~15LL; base2 &= ~15LL;          // staged bytes keep their position relative to the range's lowest offset
+  bytes1 -= base1; bytes2 -= base2;
   // Pipeline: the pairs are cut into chunks of ~48 MB of sequence; own_stream copies chunk k+1 from the host while
-  // aux_stream packs and scores chunk k (the staging pool is sized for the whole batch, so chunks need no double
-  // buffering: every byte keeps its absolute position).  With pinned host buffers the call runs at PCIe speed.
+  // aux_stream packs and scores chunk k (the staging pool is sized for the whole range, so chunks need no double
+  // buffering: every byte keeps its relative position).  With pinned host buffers the call runs at PCIe speed.
   const swb200_params pv = p ? *p : swb200_params{1, -1, 1, 1};
   const swb200_options ov = opt ? *opt : swb200_options{};
   if ((rc = check_params(pv))) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   cudaStream_t sc = c->own_stream, sk = c->aux_stream;
   const size_t np = (size_t)npairs;
@@ -1152,8 +1284,9 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
   struct Chunk { long long k0, k1, lo1, hi1, lo2, hi2; };
   std::vector<Chunk> chunks;
   {
-    const char* ov_chunk = getenv("SWB200_BATCH_CHUNK_BYTES");       // tests: force many small chunks
-    const long long target = ov_chunk ? std::max(1LL, atoll(ov_chunk)) : 48LL << 20;
+    const long long forced = settings().batch_chunk_bytes;
+    const bool ov_chunk = forced > 0;                                // tests: force many small chunks
+    const long long target = ov_chunk ? forced : 48LL << 20;
     const long long min_pairs = ov_chunk ? 1 : 1024;
     Chunk cur{0, 0, LLONG_MAX, 0, LLONG_MAX, 0};
     long long acc = 0;
@@ -1184,15 +1317,16 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
   bool first = true;
   for (size_t ci = 0; ci < chunks.size(); ++ci) {
     const Chunk& ch = chunks[ci];
-    if (ch.hi1 > ch.lo1) SWB_CUDA(cudaMemcpyAsync(c->hb_seq1 + ch.lo1, seq1_all + ch.lo1, (size_t)(ch.hi1 - ch.lo1), cudaMemcpyHostToDevice, sc));
-    if (ch.hi2 > ch.lo2) SWB_CUDA(cudaMemcpyAsync(c->hb_seq2 + ch.lo2, seq2_all + ch.lo2, (size_t)(ch.hi2 - ch.lo2), cudaMemcpyHostToDevice, sc));
+    if (ch.hi1 > ch.lo1) SWB_CUDA(cudaMemcpyAsync(c->hb_seq1 + (ch.lo1 - base1), seq1_all + ch.lo1, (size_t)(ch.hi1 - ch.lo1), cudaMemcpyHostToDevice, sc));
+    if (ch.hi2 > ch.lo2) SWB_CUDA(cudaMemcpyAsync(c->hb_seq2 + (ch.lo2 - base2), seq2_all + ch.lo2, (size_t)(ch.hi2 - ch.lo2), cudaMemcpyHostToDevice, sc));
     SWB_CUDA(cudaEventRecord(c->chunk_events[ci], sc));
     SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
     if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
     const long long nk = ch.k1 - ch.k0;
     const long long total = nk * (q_stride + t_stride);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);
-    swb::launch_pack_batch(c->hb_seq1, c->hb_off1 + ch.k0, c->hb_len1 + ch.k0, c->hb_seq2, c->hb_off2 + ch.k0, c->hb_len2 + ch.k0, nk,
+    // the pack kernel adds the absolute offsets: hand it the staging pointers shifted back by the range's base
+    swb::launch_pack_batch(c->hb_seq1 - base1, c->hb_off1 + ch.k0, c->hb_len1 + ch.k0, c->hb_seq2 - base2, c->hb_off2 + ch.k0, c->hb_len2 + ch.k0, nk,
                            q_stride, t_stride, c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0,
                            c->hb_tl + ch.k0, banded ? 1 : 0, c->d_result, blocks, sk);
     SWB_CUDA(cudaGetLastError());
@@ -1229,52 +1363,107 @@ int swb200_score_banded_batch(const unsigned char* seq1_all, const long long* of
   return score_batch_host(seq1_all, off1, len1, seq2_all, off2, len2, npairs, p, opt, 1, band_lo, band_hi, scores_out);
 }
 
+int swb200_score_banded(const unsigned char* seq1, int n, const unsigned char* seq2, int m, int band_lo, int band_hi,
+                        const swb200_params* p, int* score_out) {
+  if (n < 0 || m < 0 || !score_out || (n > 0 && !seq1) || (m > 0 && !seq2)) return fail(SWB200_ERR_ARG, "bad sequence arguments");
+  if (band_hi - band_lo != swb::kBandWidth - 1) return fail(SWB200_ERR_ARG, "the banded kernel handles exactly 64 diagonals");
+  *score_out = 0;
+  if (n == 0 || m == 0) { if (p) { int rc = check_params(*p); if (rc) return rc; } return SWB200_OK; }
+  const long long off = 0;
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  return score_batch_host_ctx(c, seq1, &off, &n, seq2, &off, &m, 1, p, nullptr, 1, band_lo, band_hi, score_out);
+}
+
 // ---- one pair over a ring of GPUs (one swb200_ring per GPU / per process) -------------------------
 int swb200_ring_create(swb200_ctx* c, int rank, int world, long long max_stream_len, swb200_ring** ring_out,
                        unsigned char handle_out[64]) {
   if (!c || !ring_out || !handle_out || world < 1 || rank < 0 || rank >= world || max_stream_len < 1)
     return fail(SWB200_ERR_ARG, "bad ring arguments");
+  *ring_out = nullptr;
   std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
-  swb200_ring* r = new swb200_ring();
+  std::unique_ptr<swb200_ring, RingDeleter> r(new swb200_ring());
   r->ctx = c; r->rank = rank; r->world = world;
-  const long long len = 1LL << log2_ceil(max_stream_len + 4 * 96 + 2 * swb::kChunk);
-  r->entries = 2 * (size_t)len;
+  r->len = (size_t)1 << log2_ceil(max_stream_len + 4 * 96 + 2 * swb::kRebaseBlock);
+  r->entries = 8 * r->len;
   SWB_CUDA(cudaMalloc(&r->inbound, r->entries * sizeof(uint2)));
   SWB_CUDA(cudaMemset(r->inbound, 0, r->entries * sizeof(uint2)));
   cudaIpcMemHandle_t h;
   SWB_CUDA(cudaIpcGetMemHandle(&h, r->inbound));
   static_assert(sizeof(h) == 64, "CUDA IPC handle size");
   memcpy(handle_out, &h, 64);
-  *ring_out = r;
+  if (world == 1) { r->next = r->inbound; r->root = r->inbound; }
+  *ring_out = r.release();
+  return SWB200_OK;
+}
+
+static int ring_open_ipc(swb200_ring* r, const unsigned char handle[64], uint2** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  SWB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *out = reinterpret_cast<uint2*>(p);
   return SWB200_OK;
 }
 
 int swb200_ring_connect(swb200_ring* r, const unsigned char next_handle[64]) {
   if (!r || !next_handle) return fail(SWB200_ERR_ARG, "bad ring arguments");
   std::lock_guard<std::mutex> lk(r->ctx->mu);
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(r->ctx->device));
-  if (r->world == 1) { r->next = r->inbound; return SWB200_OK; }
-  cudaIpcMemHandle_t h;
-  memcpy(&h, next_handle, 64);
-  void* p = nullptr;
-  SWB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-  r->next = reinterpret_cast<uint2*>(p);
+  if (r->world == 1) return SWB200_OK;
+  int rc = ring_open_ipc(r, next_handle, &r->next);
+  if (rc) return rc;
   r->next_is_ipc = true;
+  return SWB200_OK;
+}
+
+int swb200_ring_connect_root(swb200_ring* r, const unsigned char root_handle[64]) {
+  if (!r || !root_handle) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  std::lock_guard<std::mutex> lk(r->ctx->mu);
+  DeviceGuard guard;
+  SWB_CUDA(cudaSetDevice(r->ctx->device));
+  if (r->world == 1 || r->rank == 0) { r->root = r->inbound; return SWB200_OK; }
+  if (r->rank == r->world - 1 && r->next) { r->root = r->next; return SWB200_OK; }   // already mapped: the next rank IS the root
+  int rc = ring_open_ipc(r, root_handle, &r->root);
+  if (rc) return rc;
+  r->root_is_ipc = true;
+  return SWB200_OK;
+}
+
+static int ring_enable_peer(swb200_ring* r, swb200_ring* other) {
+  if (other->ctx->device == r->ctx->device) return SWB200_OK;
+  SWB_CUDA(cudaSetDevice(r->ctx->device));
+  int can = 0;
+  SWB_CUDA(cudaDeviceCanAccessPeer(&can, r->ctx->device, other->ctx->device));
+  if (!can) return fail(SWB200_ERR_CUDA, "no peer access between the ring's devices");
+  cudaError_t e = cudaDeviceEnablePeerAccess(other->ctx->device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+    return fail(SWB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+  cudaGetLastError();
   return SWB200_OK;
 }
 
 int swb200_ring_connect_local(swb200_ring* r, swb200_ring* next) {
   if (!r || !next) return fail(SWB200_ERR_ARG, "bad ring arguments");
   if (next->entries != r->entries) return fail(SWB200_ERR_ARG, "rings of different capacity");
-  if (next->ctx->device != r->ctx->device) {
-    SWB_CUDA(cudaSetDevice(r->ctx->device));
-    cudaError_t e = cudaDeviceEnablePeerAccess(next->ctx->device, 0);
-    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-      return fail(SWB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
-    cudaGetLastError();
-  }
+  DeviceGuard guard;
+  int rc = ring_enable_peer(r, next);
+  if (rc) return rc;
   r->next = next->inbound;
+  return SWB200_OK;
+}
+
+int swb200_ring_connect_root_local(swb200_ring* r, swb200_ring* root) {
+  if (!r || !root) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  if (root->entries != r->entries || root->rank != 0) return fail(SWB200_ERR_ARG, "not the root ring of this ring");
+  DeviceGuard guard;
+  int rc = ring_enable_peer(r, root);
+  if (rc) return rc;
+  r->root = root->inbound;
   return SWB200_OK;
 }
 
@@ -1291,22 +1480,283 @@ int swb200_ring_score_device(swb200_ring* r, const unsigned char* d_seq1, long l
   if ((rc = check_params(p))) return rc;
   if (n < 1 || m < 1) return fail(SWB200_ERR_ARG, "ring scoring needs non-empty sequences");
   if (o.lanes != 16 && o.lanes != 32) return fail(SWB200_ERR_ARG, "ring scoring needs an explicit lane width (16 or 32)");
+  DeviceGuard guard;
   SWB_CUDA(cudaSetDevice(c->device));
   c->info = swb200_run_info{};
   c->info.cells = n * m;
   r->calls += 1;
-  RingCfg cfg{r->rank, r->world, r->inbound, r->next, r->entries, r->calls < 16384 ? r->calls : 0u};
+  r->combine = RingCombine{};
+  RingCfg cfg{r->rank, r->world, r->inbound, r->next, r->len, r->calls < 16384 ? r->calls : 0u, r->root, &r->combine};
   const int lanes = (o.lanes == 16 && o.rebase > 0) ? 17 : o.lanes;
   return run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, nullptr, (cudaStream_t)stream, partial_score_out, status_out, &cfg);
 }
 
+int swb200_ring_combine_pending(swb200_ring* r) { return r && r->combine.pending ? 1 : 0; }
+
+int swb200_ring_combine(swb200_ring* r, void* stream, int* crossing_score_out) {
+  if (!r || !crossing_score_out) return fail(SWB200_ERR_ARG, "bad ring arguments");
+  *crossing_score_out = 0;
+  swb200_ctx* c = r->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const RingCombine cb = r->combine;
+  r->combine.pending = false;
+  if (!cb.pending || r->rank != 0) return SWB200_OK;      // only the root holds the two middle rows
+  DeviceGuard guard;
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint2* ff = r->inbound + 4 * r->len;
+  const uint2* fb = r->inbound + 6 * r->len;
+  const uint2* bf = cb.rebased ? ff + (size_t)cb.ext_len + (size_t)((cb.NB0 - 1) & 3) * (size_t)(cb.ext_len / 4) : nullptr;
+  const uint2* bb = cb.rebased ? fb + (size_t)cb.ext_len + (size_t)((cb.NB1 - 1) & 3) * (size_t)(cb.ext_len / 4) : nullptr;
+  SWB_CUDA(cudaMemsetAsync(c->d_result + 28, 0, sizeof(int), s));
+  combine_two_sided_kernel<<<2 * c->sms, 256, 0, s>>>(ff, fb, cb.LT, cb.skew, cb.linear, cb.gap_init, cb.gap_ext, bf, bb,
+                                                      c->d_result + 28);
+  SWB_CUDA(cudaGetLastError());
+  SWB_CUDA(cudaMemcpyAsync(c->h_result + 28, c->d_result + 28, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaStreamSynchronize(s));
+  c->info.aux_launches += 1;
+  *crossing_score_out = c->h_result[28];
+  return SWB200_OK;
+}
+
 void swb200_ring_destroy(swb200_ring* r) {
   if (!r) return;
+  DeviceGuard guard;
   cudaSetDevice(r->ctx->device);
+  if (r->root_is_ipc && r->root) cudaIpcCloseMemHandle(r->root);
   if (r->next_is_ipc && r->next) cudaIpcCloseMemHandle(r->next);
   cudaFree(r->inbound);
   delete r;
 }
+
+}  // extern "C"
+
+// ---- several GPUs driven from ONE host process (the reference's caller is a single-threaded C++ loop,
+//      TestFileWithGPU.cpp:57-94): swb200_set_devices(G) makes the host-buffer entry points use G GPUs --
+//      a long pair is spread over an in-process ring (one host thread per GPU for the duration of the call, peer
+//      access instead of IPC handles), a batch is cut into G contiguous ranges of pairs, one copy/compute pipeline
+//      per GPU, no communication.
+namespace {
+
+struct Pool {
+  std::mutex mu;                       // one pool call at a time
+  std::vector<swb200_ctx*> ctx;        // device g = ctx[g]
+  std::vector<swb200_ring*> ring;
+  long long ring_stream_len = 0;
+  swb200_run_info info{};              // what the last pool call ran (swb200_last_run(NULL, ..))
+  bool info_valid = false;
+};
+Pool g_pool;
+
+// fn(g) on one host thread per device; the first failure wins and its message is carried over to the caller's thread
+template <class F>
+int pool_parallel(int n, F fn) {
+  std::vector<int> rc((size_t)n, 0);
+  std::vector<std::string> err((size_t)n);
+  std::vector<std::thread> th;
+  th.reserve((size_t)n);
+  for (int g = 0; g < n; ++g)
+    th.emplace_back([&rc, &err, &fn, g] {
+      rc[(size_t)g] = fn(g);
+      if (rc[(size_t)g]) err[(size_t)g] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < n; ++g)
+    if (rc[(size_t)g]) return fail(rc[(size_t)g], "device " + std::to_string(g) + ": " + err[(size_t)g]);
+  return SWB200_OK;
+}
+
+void pool_clear_locked() {
+  for (swb200_ring* r : g_pool.ring) swb200_ring_destroy(r);
+  g_pool.ring.clear();
+  g_pool.ring_stream_len = 0;
+  for (swb200_ctx* c : g_pool.ctx) swb200_ctx_destroy(c);
+  g_pool.ctx.clear();
+  g_pool.info_valid = false;
+}
+
+int pool_rings_locked(long long stream_len) {
+  const int G = (int)g_pool.ctx.size();
+  if ((int)g_pool.ring.size() == G && g_pool.ring_stream_len >= stream_len) return SWB200_OK;
+  for (swb200_ring* r : g_pool.ring) swb200_ring_destroy(r);
+  g_pool.ring.clear();
+  g_pool.ring_stream_len = 0;
+  const long long want = std::max<long long>(stream_len, 1 << 16);
+  int rc;
+  for (int g = 0; g < G; ++g) {
+    swb200_ring* r = nullptr;
+    unsigned char handle[64];
+    if ((rc = swb200_ring_create(g_pool.ctx[(size_t)g], g, G, want, &r, handle))) return rc;
+    g_pool.ring.push_back(r);
+  }
+  for (int g = 0; g < G; ++g) {
+    if ((rc = swb200_ring_connect_local(g_pool.ring[(size_t)g], g_pool.ring[(size_t)((g + 1) % G)]))) return rc;
+    if ((rc = swb200_ring_connect_root_local(g_pool.ring[(size_t)g], g_pool.ring[0]))) return rc;
+  }
+  g_pool.ring_stream_len = want;
+  return SWB200_OK;
+}
+
+// One long host pair over the pool's ring.  *handled = false: not a case for the ring (bytes other than A,C,G,T),
+// the caller scores it on one GPU.
+int pool_score_pair(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m, const swb200_params* pp,
+                    const swb200_options* oo, int* score_out, bool* handled) {
+  *handled = true;
+  const int G = (int)g_pool.ctx.size();
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  const swb200_options o = oo ? *oo : swb200_options{};
+  int rc;
+  if ((rc = check_params(p))) return rc;
+  const bool stream_is_shorter = o.orient == 0;
+  if ((rc = pool_rings_locked(stream_is_shorter ? std::min(n, m) : std::max(n, m)))) return rc;
+  // every GPU gets both sequences (G uploads in parallel, one per PCIe link)
+  const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
+  rc = pool_parallel(G, [&](int g) -> int {
+    swb200_ctx* c = g_pool.ctx[(size_t)g];
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard guard;
+    SWB_CUDA(cudaSetDevice(c->device));
+    int r;
+    if ((r = grow(c->d_ascii, c->ascii_cap, off2 + (size_t)m + 256, false, c->own_stream))) return r;
+    SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, c->own_stream));
+    SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, c->own_stream));
+    return SWB200_OK;
+  });
+  if (rc) return rc;
+  // lane-width policy of swb200_score (score_device_locked), decided once for all ranks
+  struct Attempt { int lanes, rebase; };
+  std::vector<Attempt> attempts;
+  const long long bound = (long long)p.match * std::min(n, m);
+  const bool rb_ok = o.rebase >= 0 && rebase_is_safe(p, o.rows ? o.rows : 16);
+  if (o.lanes == 32) attempts.push_back({32, -1});
+  else if (o.lanes == 16) attempts.push_back({16, o.rebase});
+  else {
+    if (bound <= 8LL * 32767 && o.rebase <= 0) attempts.push_back({16, -1});
+    if (rb_ok) attempts.push_back({16, 1});
+    attempts.push_back({32, -1});
+  }
+  for (const Attempt& at : attempts) {
+    std::vector<int> part((size_t)G, 0), status((size_t)G, 0);
+    swb200_options oa = o;
+    oa.lanes = at.lanes; oa.rebase = at.rebase;
+    rc = pool_parallel(G, [&](int g) -> int {
+      swb200_ctx* c = g_pool.ctx[(size_t)g];
+      return swb200_ring_score_device(g_pool.ring[(size_t)g], c->d_ascii, n, c->d_ascii + off2, m, &p, &oa, c->own_stream,
+                                      &part[(size_t)g], &status[(size_t)g]);
+    });
+    if (rc) return rc;
+    int best = 0, st = 0;
+    float ms = 0;
+    for (int g = 0; g < G; ++g) {
+      best = std::max(best, part[(size_t)g]);
+      st |= status[(size_t)g];
+      ms = std::max(ms, g_pool.ctx[(size_t)g]->info.engine_ms);
+    }
+    int crossing = 0;
+    const bool two_sided = swb200_ring_combine_pending(g_pool.ring[0]) != 0;
+    if ((rc = swb200_ring_combine(g_pool.ring[0], g_pool.ctx[0]->own_stream, &crossing))) return rc;
+    for (int g = 1; g < G; ++g) g_pool.ring[(size_t)g]->combine.pending = false;
+    best = std::max(best, crossing);
+    if (st & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off between GPUs timed out");
+    if (st & swb::STATUS_BAD_SYMBOL) { *handled = false; return SWB200_OK; }
+    if (st & (swb::STATUS_S16_OVERFLOW | swb::STATUS_REBASE_RANGE)) {
+      if (o.lanes == 16) return fail(SWB200_ERR_RANGE, "score leaves the 16-bit lane range");
+      continue;
+    }
+    g_pool.info = g_pool.ctx[0]->info;
+    g_pool.info.engine_ms = ms;          // max over the GPUs
+    g_pool.info.two_sided = two_sided;
+    g_pool.info.ctas *= G; g_pool.info.warps *= G;
+    g_pool.info_valid = true;
+    *score_out = best;
+    return SWB200_OK;
+  }
+  return fail(SWB200_ERR_RANGE, "no lane width could score this pair");
+}
+
+}  // namespace
+
+static int score_pair_on_pool(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                              const swb200_params* p, const swb200_options* opt, int* score_out) {
+  std::lock_guard<std::mutex> pl(g_pool.mu);
+  g_pool.info_valid = false;
+  if (g_pool.ctx.size() < 2) return 1;
+  const long long min_cells = settings().ring_min_cells;
+  if ((double)n * (double)m < (double)min_cells) return 1;
+  bool handled = true;
+  const int rc = pool_score_pair(seq1, n, seq2, m, p, opt, score_out, &handled);
+  if (rc) return rc;
+  return handled ? SWB200_OK : 1;
+}
+
+static int score_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                            const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                            const swb200_params* p, const swb200_options* opt, int banded, int band_lo, int band_hi,
+                            int* scores_out) {
+  {
+    std::unique_lock<std::mutex> pl(g_pool.mu);
+    const int G = (int)g_pool.ctx.size();
+    if (G > 1 && npairs >= 2LL * G) {
+      // contiguous ranges of pairs, one per GPU (pair_id / ceil(P / G)); no data-path communication
+      const long long per = (npairs + G - 1) / G;
+      int rc = pool_parallel(G, [&](int g) -> int {
+        const long long k0 = std::min<long long>(npairs, (long long)g * per), k1 = std::min<long long>(npairs, k0 + per);
+        return score_batch_host_ctx(g_pool.ctx[(size_t)g], seq1_all, off1 + k0, len1 + k0, seq2_all, off2 + k0, len2 + k0, k1 - k0, p, opt,
+                                    banded, band_lo, band_hi, scores_out + k0);
+      });
+      if (rc) return rc;
+      g_pool.info = g_pool.ctx[0]->info;
+      g_pool.info.cells = 0; g_pool.info.engine_ms = 0; g_pool.info.engine_launches = 0; g_pool.info.aux_launches = 0;
+      for (int g = 0; g < G; ++g) {
+        const swb200_run_info& gi = g_pool.ctx[(size_t)g]->info;
+        g_pool.info.cells += gi.cells; g_pool.info.engine_ms = std::max(g_pool.info.engine_ms, gi.engine_ms);
+        g_pool.info.engine_launches += gi.engine_launches; g_pool.info.aux_launches += gi.aux_launches;
+      }
+      g_pool.info_valid = true;
+      return SWB200_OK;
+    }
+    g_pool.info_valid = false;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  return score_batch_host_ctx(c, seq1_all, off1, len1, seq2_all, off2, len2, npairs, p, opt, banded, band_lo, band_hi, scores_out);
+}
+
+static bool pool_last_run(swb200_run_info* info) {
+  std::lock_guard<std::mutex> pl(g_pool.mu);
+  if (!g_pool.info_valid) return false;
+  *info = g_pool.info;
+  return true;
+}
+
+extern "C" {
+
+int swb200_set_devices(int count) {
+  std::lock_guard<std::mutex> pl(g_pool.mu);
+  if (count < 0) return fail(SWB200_ERR_ARG, "negative device count");
+  const int avail = swb200_device_count();
+  if (count > 1 && count > avail)
+    return fail(SWB200_ERR_ARG, "asked for " + std::to_string(count) + " devices, " + std::to_string(avail) + " present");
+  pool_clear_locked();
+  if (count <= 1) return SWB200_OK;
+  for (int g = 0; g < count; ++g) {
+    swb200_ctx* c = nullptr;
+    const int rc = swb200_ctx_create(g, &c);
+    if (rc) { const std::string msg = g_err; pool_clear_locked(); return fail(rc, msg); }
+    g_pool.ctx.push_back(c);
+  }
+  return SWB200_OK;
+}
+
+int swb200_get_devices(void) {
+  std::lock_guard<std::mutex> pl(g_pool.mu);
+  return std::max<int>(1, (int)g_pool.ctx.size());
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- the reference's names (algoGPU.h:5-9, SmithDiagonalGPUrefactored.cu:174) ---------------------
 int SequentialSmithWatermanScoreGPU(unsigned char* seq1, unsigned char* seq2, int len1, int len2) {

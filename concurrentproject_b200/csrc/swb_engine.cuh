@@ -38,6 +38,12 @@ SWB_HD constexpr int step_unroll(double instr_per_row, int rows, int big) { retu
 #define SWB_STEP_UNROLL32 8
 #endif
 constexpr int kStepUnroll32 = SWB_STEP_UNROLL32;   // 32-bit engine
+// Measurement builds only (bench/knock.sh): SWB_KNOCK is a bit mask of step-loop components to leave out -- scores are
+// WRONG, the time difference is what the component costs.  1 boundary store, 2 inbox load + select, 4 table load,
+// 8 shuffle, 16 running best, 32 chunk prologue work (table fill, polls).
+#ifndef SWB_KNOCK
+#define SWB_KNOCK 0
+#endif
 constexpr int kChunk = 32;     // steps between boundary polls / table refills
 constexpr int kTabRing = 256;  // per-warp ring of substitution tables (one per T position), kept twice
 constexpr int kInbox = 64;     // per-warp ring of validated top-boundary values
@@ -72,7 +78,8 @@ struct EngineParams {
   int match, mismatch, gap_init, gap_ext;
   long long spin_limit;         // polls before a waiting warp gives up (sets STATUS_SPIN_TIMEOUT)
   int dbg;                      // timing experiments only: 1 = no boundary stores, 2 = no boundary polls
-  long long* prof;              // optional [warps_local][4]: cycles in prologue, cycles in steps, failed polls, chunks
+  long long* prof;              // optional [warps_local][8]: cycles in prologue, cycles in steps, failed polls, chunks,
+                                //   globaltimer at the first band's first chunk / at its end, SM id
   int* cand;                    // TRACK kernels: per band {best H, its T position, its Q row} (first in column-major order)
 };
 
@@ -171,8 +178,13 @@ SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned lo
 SWB_HD int hi_half_max(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a > b ? a : b; }
 SWB_HD int lo_half_min(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a < b ? a : b; }
 
-template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true>
+//  PIPE: software-pipelined chunk loop.  The boundary entries of chunk c+1 are loaded when chunk c starts and are
+//  validated, translated and put into the shared-memory inbox HALF WAY THROUGH chunk c (together with the
+//  substitution tables of chunk c+1), so that the load -> vote -> store -> sync -> load latency chain of the chunk
+//  prologue overlaps the step loop instead of standing between two chunks.
+template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, bool PIPE = false>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
+  static_assert(SLACK >= 0 && SLACK <= 2, "a shuffled boundary value is consumed 0, 1 or 2 steps after it was sent");
   constexpr int SK = 2 + SLACK;        // T positions between neighbouring lanes
   constexpr int SKEW = 31 * SK + 1;    // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
   constexpr int kU = step_unroll(MODE == 0 ? (RB ? 8.5 : 7.5) : (RB ? 5.5 : 4.5), R, kStepUnroll);
@@ -241,7 +253,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     uint32_t Ho[R], E[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
-    uint32_t Fbot = nopen, up_prev = nopen, xsend = nopen, yold = nopen, Thi = padw;
+    uint32_t Fbot = nopen, up_prev = nopen, xsend = nopen, yold = nopen, yold2 = nopen, Thi = padw;
     if (RB) { base = 0; floorw = 0; best0 = 0; best1 = 0; }   // every band starts at T position 0, where all scores are small
     // base entries live in the second half of a link ring: one {base, tag} per kRebaseBlock producer steps
     // (on the full-length ext stream, which restarts every band, four bands' worth of base entries rotate, so a
@@ -273,22 +285,53 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       if (RB) bpref = ld_entry(in_bases + ((j >> 8) & inb_mask));
     }
     if (SLACK && !zero_src) {
-      // With the slack step lane 0 consumes at step i what was shuffled at step i-1; nothing is shuffled before
-      // step 0, so the boundary value of T position 0 is handed to lane 0 here.  (Every band starts with base 0,
-      // so no translation is needed in re-based mode.)
-      const long long j0 = in_base + SKEW;
-      const uint32_t v0 = wait_entry(P, w, true, in + (j0 & in_mask), in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu),
-                                     ld_entry(in + (j0 & in_mask)), wt);
-      if (lane == 0) yold = v0;
+      // With slack steps lane 0 consumes at step i what was shuffled at step i-SLACK; nothing is shuffled before
+      // step 0, so the boundary values of T positions 0 .. SLACK-1 are handed to lane 0 here.  (Every band starts
+      // with base 0, so no translation is needed in re-based mode.)
+#pragma unroll
+      for (int d = 0; d < SLACK; ++d) {
+        if (d < LT) {                                               // warp-uniform
+          const long long j0 = in_base + SKEW + d;
+          const uint32_t v0 = wait_entry(P, w, true, in + (j0 & in_mask), in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu),
+                                         ld_entry(in + (j0 & in_mask)), wt);
+          if (lane == 0) { if (d == SLACK - 1) yold = v0; else yold2 = v0; }
+        }
+      }
+    }
+    if (PIPE) {
+      // chunk 0's top boundary is fetched here, before the loop; every later chunk's half way through the chunk before
+      const int q = SLACK + lane;
+      uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
+      if (!zero_src) {
+        const bool need = q < LT;
+        const long long j = in_base + q + SKEW;
+        const uint32_t got = wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
+        if (need) v = got;
+        if (RB) {
+          const long long bj = j >> 8;
+          const uint32_t pb = wait_entry(P, w, need, in_bases + (bj & inb_mask), in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
+          if (need) v = add16x2(v, pack2((int)pb - base));          // base == 0 here
+        }
+      }
+      sm->inbox[q & (kInbox - 1)] = v;
+      sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
     }
 
+#if SWB_DEVICE_CODE
+    if (SWB_PROF && lane == 31 && SWB_PROF[8 * lw + 4] == 0) {
+      unsigned long long gt; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      SWB_PROF[8 * lw + 4] = (long long)gt; SWB_PROF[8 * lw + 6] = (long long)smid;
+    }
+#endif
     for (int i0 = 0; i0 < nsteps; i0 += kChunk) {
 #if SWB_DEVICE_CODE
       const long long tp0 = SWB_PROF ? clock64() : 0;
       const long long bud0 = wt.budget;
 #endif
       // (a) substitution tables for T positions [i0+32, i0+64); fetch the word after that
-      {
+      auto fill_tables = [&]() {
         const int q = i0 + kChunk + lane;
         uint32_t c = 4;
         if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
@@ -296,7 +339,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         sm->tab[q & (kTabRing - 1)] = tw;
         sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
         twpref = (q + kChunk < LT) ? ld_early_u64(SWB_T_PACKED + ((q + kChunk) >> 5)) : 0ull;
-      }
+      };
+      if (!PIPE && !(SWB_KNOCK & 32)) fill_tables();
       // (a') re-based mode: every kRebaseBlock steps re-centre the registers around the live score level
       if (RB && (i0 & (kRebaseBlock - 1)) == 0) {
         if (i0 > 0) {
@@ -316,8 +360,17 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
             for (int r = 0; r < R; ++r) { Ho[r] = add16x2(Ho[r], dw); E[r] = add16x2(E[r], dw); }
             Fbot = add16x2(Fbot, dw); up_prev = add16x2(up_prev, dw); xsend = add16x2(xsend, dw); yold = add16x2(yold, dw);
+            yold2 = add16x2(yold2, dw);
             base += delta;
             floorw = pack2(-base > -30000 ? -base : -30000);
+            if (PIPE) {
+              // this chunk's inbox entries were translated to the old base half a chunk ago (by this same lane)
+              const int q = i0 + SLACK + lane;
+              uint32_t v = add16x2(nopen, floorw);
+              if (!zero_src && q < LT) v = add16x2(sm->inbox[q & (kInbox - 1)], dw);
+              sm->inbox[q & (kInbox - 1)] = v;
+              sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
+            }
           }
         }
         // tell the band below which base the entries of this block are relative to
@@ -328,7 +381,40 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       bool spec = false;
       const uint2* spec_e = in;
       const uint2* spec_b = in;
-      {
+      // PIPE: the same for the NEXT chunk, called half way through this one; its entries were requested at (b0)
+      long long pj = 0;
+      bool pneed = false;
+      auto fill_inbox_next = [&]() {
+        const int q = i0 + kChunk + SLACK + lane;
+        uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
+        if (!zero_src) {                                                  // warp-uniform branch
+          const uint32_t got = wait_entry(P, w, pneed, in + (pj & in_mask), in_tag | ((uint32_t)(pj >> in_shift) & 0xFFu), epref, wt);
+          if (pneed) v = got;
+          if (RB) {
+            const long long bj = pj >> 8;
+            const uint32_t pb = wait_entry(P, w, pneed, in_bases + (bj & inb_mask), in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
+            if (pneed) {
+              const int diff = (int)pb - base;
+              if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
+              v = add16x2(v, pack2(diff));
+            }
+          }
+        }
+        sm->inbox[q & (kInbox - 1)] = v;
+        sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
+      };
+      if (PIPE) {
+        // (b0) request the next chunk's entries now; they are looked at 16 steps from here
+        const int q = i0 + kChunk + SLACK + lane;
+        pneed = q < LT;
+        pj = in_base + q + SKEW;
+        if (!zero_src && pneed) {
+          epref = ld_entry(in + (pj & in_mask));
+          if (RB) bpref = ld_entry(in_bases + ((pj >> 8) & inb_mask));
+        }
+        if (lane == 0 && (i0 & 255) == 0)
+          st_progress(my_progress, (unsigned long long)(sbase + i0 + SLACK + kChunk));
+      } else {
         const int q = i0 + SLACK + lane;
         uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
         if (!zero_src) {                                                  // warp-uniform branch
@@ -376,11 +462,12 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       auto step = [&](const int k) {
         const uint32_t Tlo = Tnext;
         const uint32_t xin = xnext;
-        Tnext = tabp[k + 1];
-        xnext = inbp[k + 1];
-        const uint32_t xs = last_lane ? xin : xsend;
-        const uint32_t ynew = w.shfl(xs, src_lane);
-        const uint32_t yuse = SLACK ? yold : ynew;
+        if (!(SWB_KNOCK & 4)) Tnext = tabp[k + 1]; else Tnext = Tnext * 5u + 1u;
+        if (!(SWB_KNOCK & 2)) xnext = inbp[k + 1];
+        const uint32_t xs = (SWB_KNOCK & 2) ? xsend : (last_lane ? xin : xsend);
+        const uint32_t ynew = (SWB_KNOCK & 8) ? (xs ^ (uint32_t)k) : w.shfl(xs, src_lane);
+        const uint32_t yuse = SLACK == 0 ? ynew : (SLACK == 1 ? yold : yold2);
+        yold2 = yold;
         yold = ynew;
         uint32_t upHo, F;
         if (MODE == 0) {
@@ -421,7 +508,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
             hprev = h;
             Ho[r] = add16x2(h, nopen);
             diag = old;
-            if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+            if (SWB_KNOCK & 16) { if (r == R - 1) best0 = max16x2(best0, h); }
+            else if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
           }
         } else {
           // Fewest instructions per row (used with two warps per scheduler, where the issue rate is the limit).
@@ -450,26 +538,38 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         xsend = (MODE == 0) ? prmt(Ho[R - 1], Fbot, 0x7632u) : Ho[R - 1];
         Thi = Tlo;
         // slot = producer step (always in range); steps whose T position is outside [0,LT) are never read
-        if (emit) st_entry(outp + k, xsend, otag);
+        if (!(SWB_KNOCK & 1)) { if (emit) st_entry(outp + k, xsend, otag); }
       };
       // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
       // the speculative boundary loads of the next chunk in between: the band above only has to be
       // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
 #pragma unroll (kU)
       for (int k = 0; k < kChunk / 2; ++k) step(k);
-      if (spec) epref = ld_entry(spec_e);
-      if (RB && spec) bpref = ld_entry(spec_b);
+      if (PIPE) {
+        fill_tables();
+        fill_inbox_next();
+      } else {
+        if (spec) epref = ld_entry(spec_e);
+        if (RB && spec) bpref = ld_entry(spec_b);
+      }
 #pragma unroll (kU)
       for (int k = kChunk / 2; k < kChunk; ++k) step(k);
 #if SWB_DEVICE_CODE
       if (SWB_PROF) {
         const long long tp2 = clock64();
-        long long* pr = SWB_PROF + 4 * lw;
+        long long* pr = SWB_PROF + 8 * lw;
         if (lane == 31) { pr[0] += tp1 - tp0; pr[1] += tp2 - tp1; pr[3] += 1; }
         if (lane == 31) pr[2] += bud0 - wt.budget;
       }
 #endif
     }
+#if SWB_DEVICE_CODE
+    if (SWB_PROF && lane == 31 && SWB_PROF[8 * lw + 5] == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      SWB_PROF[8 * lw + 5] = (long long)gt;
+    }
+#endif
     if (RB) {
       const int b = hi_half_max(max16x2(best0, best1)) + base;
       best_abs = best_abs > b ? best_abs : b;

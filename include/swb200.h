@@ -60,6 +60,30 @@ typedef struct {
 SWB200_API const char* swb200_last_error(void);
 SWB200_API int swb200_device_count(void);
 
+/* Debugging / measurement switches.  Each has an environment variable that is read ONCE, at the first call
+ * into the library (the scoring calls never call getenv); swb200_configure changes them afterwards:
+ *   "spin_limit" (SWB200_SPIN_LIMIT)  polls before a waiting warp gives up and the call returns SWB200_ERR_TIMEOUT
+ *   "debug" (SWB200_DEBUG)            "1": print the post-mortem of a timed-out hand-off to stderr
+ *   "prof" (SWB200_PROF)              "1": per-warp cycle counters of the pair engine to stderr; any other value: a file
+ *                                     that receives one JSON line per launch; "": off
+ *   "dbg" (SWB200_DBG)                timing experiments only (1 = no boundary stores, 2 = no boundary polls: WRONG scores)
+ *   "dump_final" (SWB200_DUMP_FINAL)  file receiving the two middle boundary rows of a two-sided sweep
+ *   "batch_chunk_bytes" (SWB200_BATCH_CHUNK_BYTES)  chunk size of the host batch calls' copy/compute pipeline (0 = default)
+ *   "ring_min_cells" (SWB200_RING_MIN_CELLS)  host-buffer pairs with at least this many cells use all devices chosen
+ *                                     with swb200_set_devices (default 2e11) */
+SWB200_API int swb200_configure(const char* key, const char* value);
+
+/* ---- several GPUs from one host process ------------------------------------------------------------
+ * The reference's caller is a single-threaded C++ loop (TestFileWithGPU.cpp:57-94).  swb200_set_devices(G) makes
+ * the HOST-buffer entry points below (and therefore the four legacy names) use devices 0 .. G-1:
+ *   - a pair with at least "ring_min_cells" cells (swb200_configure) is spread over an in-process ring of the G
+ *     GPUs (one host thread per GPU for the duration of the call, peer access over NVLink, swept from both ends);
+ *   - swb200_score_batch / swb200_score_banded_batch cut the batch into G contiguous ranges of pairs, one
+ *     copy/compute pipeline per GPU, no communication.
+ * Results are identical for every G.  count 0 or 1 = one GPU (the default).  Needs peer access between the devices. */
+SWB200_API int swb200_set_devices(int count);
+SWB200_API int swb200_get_devices(void);
+
 /* ---- one pair, HOST buffers: the call behind the four legacy names ------------------------------
  * seq1/seq2: raw bytes, not NUL-terminated, caller-owned, never modified (algoGPU.h:5-9).
  * n = len(seq1), m = len(seq2); n == 0 or m == 0 scores 0.  p == NULL means 1/-1/1/1. */
@@ -148,6 +172,9 @@ SWB200_API void swb200_batch_free(swb200_batch* batch);
  * band_lo <= j - i <= band_hi; everything outside the band is H=E=F=0 and excluded from the max.  The reference
  * has no banded mode; semantics = main.cpp:57-63 restricted to the band (oracle: oracle_gotoh_banded).
  * This kernel handles exactly 64 diagonals: band_hi == band_lo + 63. */
+/* One banded pair (the batch call with npairs = 1). */
+SWB200_API int swb200_score_banded(const unsigned char* seq1, int n, const unsigned char* seq2, int m, int band_lo,
+                                   int band_hi, const swb200_params* p, int* score_out);
 SWB200_API int swb200_score_banded_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
                                          const unsigned char* seq2_all, const long long* off2, const int* len2,
                                          long long npairs, int band_lo, int band_hi, const swb200_params* p,
@@ -174,6 +201,16 @@ SWB200_API int swb200_ring_create(swb200_ctx* ctx, int rank, int world, long lon
                                   swb200_ring** ring_out, unsigned char handle_out[64]);
 SWB200_API int swb200_ring_connect(swb200_ring* ring, const unsigned char next_handle[64]);
 SWB200_API int swb200_ring_connect_local(swb200_ring* ring, swb200_ring* next);
+/* Optional: map rank 0's region as well (its IPC handle, or its ring when it lives in this process).  With a root a
+ * long pair is swept from BOTH ends (two half problems, each a ring over all GPUs; half as many bands in a row, so
+ * half the pipeline fill); the ranks that own the two last bands store the two middle boundary rows into the root's
+ * memory.  After swb200_ring_score_device has returned on EVERY rank (the caller's barrier), rank 0 calls
+ * swb200_ring_combine and folds its result into the max over the ranks' partial scores.  Without a root the ring
+ * sweeps one-sided as before. */
+SWB200_API int swb200_ring_connect_root(swb200_ring* ring, const unsigned char root_handle[64]);
+SWB200_API int swb200_ring_connect_root_local(swb200_ring* ring, swb200_ring* root);
+SWB200_API int swb200_ring_combine_pending(swb200_ring* ring);    /* 1 if the last score call was two-sided */
+SWB200_API int swb200_ring_combine(swb200_ring* ring, void* stream, int* crossing_score_out);
 SWB200_API int swb200_ring_score_device(swb200_ring* ring, const unsigned char* d_seq1, long long n,
                                         const unsigned char* d_seq2, long long m, const swb200_params* p,
                                         const swb200_options* opt, void* stream, int* partial_score_out,

@@ -68,6 +68,8 @@ def oracle():
         lib.oracle_gotoh_span.restype = C.c_int
         lib.oracle_gotoh_mt.argtypes = sig + [C.c_int]
         lib.oracle_gotoh_mt.restype = C.c_int
+        lib.oracle_gotoh_fast.argtypes = sig + [C.c_int]
+        lib.oracle_gotoh_fast.restype = C.c_int
         lib.oracle_gotoh_banded.argtypes = sig[:4] + [C.c_int, C.c_int, C.POINTER(OracleParams), C.POINTER(C.c_int64)]
         lib.oracle_gotoh_banded.restype = C.c_int
         lib.oracle_gotoh_batch.argtypes = [C.POINTER(C.c_ubyte), C.POINTER(C.c_int64), C.POINTER(C.c_int),
@@ -150,6 +152,11 @@ def gotoh_span(s1, s2, p=DEFAULT):
 
 def gotoh_mt(s1, s2, p=DEFAULT, threads=0):
     return _call("oracle_gotoh_mt", s1, s2, p, threads)
+
+
+def gotoh_fast(s1, s2, p=DEFAULT, threads=0):
+    """oracle/gotoh_fast.c: one tile per SIMD lane; identical to gotoh_rolling, fast enough for BASELINE config 3."""
+    return _call("oracle_gotoh_fast", s1, s2, p, threads)
 
 
 def gotoh_banded(s1, s2, band_lo, band_hi, p=DEFAULT, want_cells=False):

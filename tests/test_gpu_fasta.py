@@ -61,12 +61,19 @@ def test_search_one_query_against_a_database():
     assert np.array_equal(got, want) and int(np.argmax(got)) == 123
 
 
-def test_host_batch_call_pipelines_chunks(monkeypatch):
+def test_host_batch_call_pipelines_chunks():
     """swb200_score_batch cuts the batch into chunks (copy of chunk k+1 overlaps packing and scoring chunk k):
     force ~60 chunks with ragged lengths, a shared sequence (every pair reads the same seq1 bytes) and offsets that
     are not monotone."""
     from concurrentproject_b200 import api, fasta
-    monkeypatch.setenv("SWB200_BATCH_CHUNK_BYTES", "20000")
+    api.configure("batch_chunk_bytes", "20000")
+    try:
+        _pipelined_chunk_cases(api, fasta)
+    finally:
+        api.configure("batch_chunk_bytes", "0")
+
+
+def _pipelined_chunk_cases(api, fasta):
     s1, s2 = _ragged(21, 1500, 250, 900)
     assert np.array_equal(api.score_batch(s1, s2), O.gotoh_batch(s1, s2))
     db = [bytes(rng.random_acgt(22, k, 30 + (k * 53) % 700)) for k in range(900)]
