@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the score-only Smith-Waterman/Gotoh hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|...] [--no-extra]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload is
-BASELINE config 2: one 100 000 x 100 000 pair of seeded random ACGT (seed 2), parameters 1/-1/1/1;
-its score is checked against the committed golden value (the unmodified reference's LazySmith) on
-every step.  One JSON line goes to stdout (rank 0):
+A "step" is one pass of the hot path over one batch of synthetic input.  The headline workload is BASELINE config 2:
+one 100 000 x 100 000 pair of seeded random ACGT (seed 2), parameters 1/-1/1/1, one pair per GPU (weak scaling, no
+data-path collective); its score is checked against the committed golden value on every step.  One JSON line goes to
+stdout (rank 0):
   value      device-resident GCUPS: inputs already in HBM, CUDA events around each step
              (encode kernels + wavefront kernel + 40-byte result copy), L2 flushed between steps
   e2e        the same metric through the host-buffer C ABI call the reference harness makes
@@ -15,19 +15,30 @@ every step.  One JSON line goes to stdout (rank 0):
              SURVEY.md 8d: 148 SMs x f_clk x L x V / 7, L measured by bench/intpeak.cu
   cpu_baseline  the reference's own CPU path (oracle/_ref/libref.so = unmodified
              lazySmith_parallel_threads.cpp) timed on this box's host cores, bounded sample
---impl reference runs only that CPU path, as the reference arm.
+and, unless --no-extra, two sub-records measured in the same run on the same N GPUs:
+  ring       BASELINE config 3: ONE 4 000 000 x 4 000 000 pair over the ring of all N GPUs (strong scaling; the boundary
+             stream crosses GPUs inside the kernel, peer stores over NVLink), score checked against the pinned golden
+  batch      BASELINE config 4: 10 M read/window pairs generated in HBM by the seeded device generator, sharded
+             pair-wise over the N GPUs (strong scaling, no communication), a sample checked against the oracle and a
+             64-bit checksum over all scores that is the same for every N
+--workload cfg1|n1m|ring400k|ring1m|cfg3|cfg4|cfg5 makes that workload the line itself.
+--impl reference runs only the reference's CPU path, as the reference arm.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import socket
 import sys
 import threading
 import time
 from pathlib import Path
 
 import numpy as np
+
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line is the contract
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -40,35 +51,39 @@ DPX_LANE_INSTR_PER_CLK_PER_SM = 64.0   # L: profiles/r01_intpeak.jsonl (VIMNMX3/
 INSTR_PER_CELL_VECTOR = 7.0            # SURVEY.md 8d contract figure
 N_SM = 148
 
-WORKLOADS = {
-    # name: (n, m, seed, description)
-    "cfg1": (1000, 1000, 1, "10 pairs 1000x1000 (TestFile.cpp default)"),
-    "cfg2": (100000, 100000, 2, "single pair 100000x100000, seed 2, MATCH=1 MISMATCH=-1 GAP_INIT=1 GAP_EXT=1"),
-    "n1m": (1000000, 1000000, 6, "single pair 1000000x1000000, seed 6"),
-    # one pair spread over the ring of all GPUs (strong scaling): boundary stream pushed GPU to GPU over NVLink
+PAIR_WORKLOADS = {
+    # name: (n, m, seed, pairs per step, description)
+    "cfg1": (1000, 1000, 1, 10, "10 pairs 1000x1000, seed 1 (TestFile.cpp default: 10 tests), one call per pair"),
+    "cfg2": (100000, 100000, 2, 1, "single pair 100000x100000, seed 2, MATCH=1 MISMATCH=-1 GAP_INIT=1 GAP_EXT=1"),
+    "n1m": (1000000, 1000000, 6, 1, "single pair 1000000x1000000, seed 6"),
+}
+# one pair spread over the ring of all GPUs (strong scaling): boundary stream pushed GPU to GPU over NVLink
+RING_WORKLOADS = {
     "ring400k": (400000, 400000, 7, "single pair 400000x400000, seed 7, DP bands cyclically striped over all GPUs"),
     "ring1m": (1000000, 1000000, 6, "single pair 1000000x1000000, seed 6, DP bands cyclically striped over all GPUs"),
     "cfg3": (4000000, 4000000, 3, "single pair 4000000x4000000, seed 3, DP bands cyclically striped over all GPUs"),
 }
-RING_WORKLOADS = {"ring400k", "ring1m", "cfg3"}
-# batches of independent pairs, sharded pair-wise over the GPUs (no communication): (pairs per GPU, read, window)
-BATCH_WORKLOADS = {"cfg4": (1250000, 150, 1000), "cfg4small": (100000, 150, 1000),
-                   # banded (64 diagonals): (pairs per GPU, len1, len2)
-                   "cfg5": (125000, 10000, 10000), "cfg5small": (10000, 10000, 10000)}
-BANDED = {"cfg5", "cfg5small"}
-WORKLOADS["cfg5"] = (10000, 10000, 5, "1M pairs / 8 GPUs = 125k pairs per GPU of 10 kb long reads, band -32..31 (64 diagonals), pair-sharded")
-WORKLOADS["cfg5small"] = (10000, 10000, 5, "10k pairs per GPU of 10 kb long reads, band -32..31")
-WORKLOADS["cfg4"] = (150, 1000, 4, "10M pairs / 8 GPUs = 1.25M pairs per GPU, 150 bp reads vs 1 kb windows, pair-sharded")
-WORKLOADS["cfg4small"] = (150, 1000, 4, "100k pairs per GPU, 150 bp reads vs 1 kb windows, pair-sharded")
+# batches of independent pairs, sharded pair-wise over the GPUs (no communication): (TOTAL pairs, len1, len2, seed, banded, text)
+BATCH_WORKLOADS = {
+    "cfg4": (10000000, 150, 1000, 4, False, "10M pairs, 150 bp reads vs 1 kb windows (half planted: 5% substitutions + 1% indels, half unrelated), pair-sharded"),
+    "cfg4small": (400000, 150, 1000, 4, False, "400k pairs of the cfg4 recipe"),
+    "cfg5": (1000000, 10000, 10000, 5, True, "1M pairs of 10 kb long reads (10% substitutions + 2% indels), band -32..31 (64 diagonals), pair-sharded"),
+    "cfg5small": (40000, 10000, 10000, 5, True, "40k pairs of the cfg5 recipe"),
+}
+ALL_WORKLOADS = sorted(list(PAIR_WORKLOADS) + list(RING_WORKLOADS) + list(BATCH_WORKLOADS))
 
 
 def golden_score(name):
-    if name != "cfg2":
-        return None
-    cases = json.loads((ROOT / "tests" / "golden" / "ref_scores_default.json").read_text())
-    for c in cases:
-        if c.get("config") == "cfg2":
-            return c["score"]
+    """Pinned scores: tests/golden/large_scores.json (oracle/gotoh_fast.c on the CPU: cfg2, ring400k, n1m, cfg3) and, for
+    cfg2, the unmodified reference's own LazySmith (tests/golden/ref_scores_default.json)."""
+    try:
+        big = json.loads((ROOT / "tests" / "golden" / "large_scores.json").read_text())
+        if name == "ring1m":
+            name = "n1m"
+        if name in big:
+            return int(big[name]["score"])
+    except Exception:
+        pass
     return None
 
 
@@ -114,6 +129,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def peak_gcups(f_mhz, vwidth, gpus=1):
+    return gpus * N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
+
+
 def cpu_reference_gcups(n_sample, seed, repeats=1):
     """Times the reference's own CPU path on a bounded sample of the workload; returns (gcups, kind, cores, text)."""
     import oracle_lib as O
@@ -135,24 +154,27 @@ def cpu_reference_gcups(n_sample, seed, repeats=1):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on this box's host cores.  Each step scores
+    a bounded PREFIX of the workload pair (the reference needs ~54 s for the whole cfg2 pair; its rate is flat in N,
+    SURVEY.md section 6), stated in config.sample; with --steps 1 the whole cfg2 pair is scored once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, m, seed, desc = WORKLOADS[args.workload]
-    n_s = min(n, 8000)
+    name = args.workload if args.workload in PAIR_WORKLOADS else "cfg2"
+    n, m, seed, _, desc = PAIR_WORKLOADS[name]
+    n_s = n if (args.steps == 1 and n <= 100000) else min(n, 8000)
     for _ in range(args.warmup):
         cpu_reference_gcups(2000, seed)
     t0 = time.perf_counter()
-    vals = []
     for _ in range(args.steps):
         g, kind, cores, text = cpu_reference_gcups(n_s, seed)
-        vals.append(g)
     dt = time.perf_counter() - t0
     value = n_s * n_s * args.steps / dt / 1e9
+    sample = "the whole pair" if n_s == n else f"{n_s}x{n_s} prefix of the {n}x{m} pair per step (rate over rate: the reference's GCUPS is flat in N)"
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "l2": "n/a (CPU)"},
+            "config": {"workload": name, "description": desc, "sample": sample, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": round(value, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
             "e2e": {"value": round(value, 4), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -163,55 +185,94 @@ def ncu_traffic(workload):
     committed under profiles/ (only the bench default has one); None otherwise."""
     if workload != "cfg2":
         return None
-    try:
-        d = json.load(open(ROOT / "profiles" / "r01_ncu_summary.json"))
-        return int(d["r01_cfg2_final5.ncu-rep"]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name, key in (("r02_ncu_summary.json", "r02_cfg2_final.ncu-rep"), ("r01_ncu_summary.json", "r01_cfg2_final5.ncu-rep")):
+        try:
+            d = json.load(open(ROOT / "profiles" / name))
+            return int(d[key]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from concurrentproject_b200 import api
+class Env:
+    """torch / torch.distributed plumbing of one rank (device memory, streams, the barrier; not the product)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, m, seed, desc = WORKLOADS[args.workload]
-    if args.workload in RING_WORKLOADS:
-        return run_ring(args, torch, dist, api, world, rank, local)
-    if args.workload in BATCH_WORKLOADS:
-        return run_batch(args, torch, dist, api, world, rank, local)
-    # weak scaling over pairs: rank r scores its own pair (streams 2r, 2r+1); no data-path collective
-    a_h = rng.random_acgt(seed, 2 * rank, n)
-    b_h = rng.random_acgt(seed, 2 * rank + 1, m)
-    a_d = torch.from_numpy(a_h.copy()).cuda()
-    b_d = torch.from_numpy(b_h.copy()).cuda()
-    want = golden_score(args.workload) if rank == 0 else None
-    ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from concurrentproject_b200 import api
+        self.torch, self.dist, self.api = torch, dist, api
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.current_stream()
+
+    def need_group(self):
+        """The ring front end talks torch.distributed even on one GPU."""
+        if not self.dist.is_initialized():
+            s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+            self.dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                         device_id=self.torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks_i64(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.int64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(x) for x in t.tolist()]
+
+    def close(self):
+        if self.dist.is_initialized():
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def pair_record(env, args, name):
+    """One pair (cfg1: ten pairs) per GPU per step; rank r scores its own pair(s) (streams differ per rank): weak scaling."""
+    torch, api = env.torch, env.api
+    n, m, seed, pairs, desc = PAIR_WORKLOADS[name]
+    import oracle_lib as O
+    hosts = [(rng.random_acgt(seed, 2 * (env.rank * pairs + k), n), rng.random_acgt(seed, 2 * (env.rank * pairs + k) + 1, m)) for k in range(pairs)]
+    devs = [(torch.from_numpy(a.copy()).cuda(), torch.from_numpy(b.copy()).cuda()) for a, b in hosts]
+    if name == "cfg1":
+        want = [O.gotoh_rolling(a, b) for a, b in hosts]              # every pair against the oracle
+    else:
+        want = [golden_score(name)] if env.rank == 0 else [None]
+    ctx = api.Context(env.local)
+    stream = env.stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step_device():
-        return ctx.score_device(a_d.data_ptr(), n, b_d.data_ptr(), m, stream=stream.cuda_stream, no_linear=args.no_linear)
+        return [ctx.score_device(a.data_ptr(), n, b.data_ptr(), m, stream=stream.cuda_stream, no_linear=args.no_linear) for a, b in devs]
+
+    def check(scores, what):
+        for s, w in zip(scores, want):
+            if w is not None and s != w:
+                raise SystemExit(f"bench.py: {what} score {s} != pinned {w}")
 
     for _ in range(max(args.warmup, 3)):
         s = step_device()
-    if want is not None and s != want:
-        raise SystemExit(f"bench.py: score {s} != golden {want}")
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    check(s, "device")
+    env.barrier()
+    sampler = ClockSampler(env.local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    engine_ms, launches = [], 0
+    engine_ms, launches, info = [], 0, {}
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                      # L2 flush between timed steps (outside the event pair)
         ev[k][0].record(stream)
@@ -219,255 +280,86 @@ def run_ours(args):
         ev[k][1].record(stream)
         info = ctx.last_run()
         engine_ms.append(info["engine_ms"])
-        launches += info["engine_launches"] + info["aux_launches"]
-        if want is not None and s != want:
-            raise SystemExit(f"bench.py: score {s} != golden {want}")
+        launches += pairs * (info["engine_launches"] + info["aux_launches"])
+        check(s, "device")
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     # end to end through the host-buffer call of the reference harness (TestFileWithGPU.cpp:92):
     # H2D of both sequences + encode + wavefront kernel + D2H of the result, wall clock per call
     for _ in range(2):
-        api.SmithWatermanScoreCUDA(a_h, b_h)
+        [api.SmithWatermanScoreCUDA(a, b) for a, b in hosts]
     e2e_total = 0.0
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        s2 = api.SmithWatermanScoreCUDA(a_h, b_h)
+        s2 = [api.SmithWatermanScoreCUDA(a, b) for a, b in hosts]
         e2e_total += time.perf_counter() - t1
-        if want is not None and s2 != want:
-            raise SystemExit(f"bench.py: e2e score {s2} != golden {want}")
-
-    t = torch.tensor([dev_ms, e2e_total * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    cells = float(n) * float(m)
-    value = cells * world * args.steps / (dev_ms * 1e-3) / 1e9
-    e2e_val = cells * world * args.steps / (e2e_ms * 1e-3) / 1e9
-    if rank == 0:
-        k_ms = float(np.mean(engine_ms))
-        f_mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965
-        vwidth = 2 if info["lanes"] == 16 else 1
-        peak = N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
-        achieved = cells / (k_ms * 1e-3) / 1e9
-        cpu_g, kind, cores, text = cpu_reference_gcups(min(n, 12000), seed)
-        line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "s16x2" if info["lanes"] == 16 else "s32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "pairs_per_gpu": 1,
-                       "l2": "flushed between timed steps (256 MiB write)", "kernel": info,
-                       "score_checked_against_golden": want is not None},
-            "clocks": clocks,
-            "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(n + m), "d2h_bytes_per_step": 40,
-                    "call": "SmithWatermanScoreCUDA(host bytes) via libswb200.so C ABI, wall clock"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
-                         "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); traffic = DRAM bytes per launch "
-                                 f"from the committed ncu capture (profiles/r01_ncu_summary.json), algorithmic input is {(n + m) // 4} bytes, "
-                                 f"the boundary rows of the bands live in L2; peak = 148 SM x {f_mhz} MHz x "
-                                 f"L={DPX_LANE_INSTR_PER_CLK_PER_SM:.0f} DPX lane-instr/clk/SM (measured, bench/intpeak.cu) x V={vwidth} / 7 "
-                                 "instr per cell vector (SURVEY.md 8d); not an HBM- or tensor-bound kernel"},
-            "cpu_baseline": {"value": round(cpu_g, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        check(s2, "e2e")
+    dev_ms, e2e_ms = env.max_over_ranks([dev_ms, e2e_total * 1e3])
+    cells = float(n) * float(m) * pairs
+    value = cells * env.world * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_val = cells * env.world * args.steps / (e2e_ms * 1e-3) / 1e9
+    if env.rank != 0:
+        return None
+    k_ms = float(np.mean(engine_ms))
+    f_mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965
+    vwidth = 2 if info["lanes"] == 16 else 1
+    peak = peak_gcups(f_mhz, vwidth)
+    achieved = float(n) * float(m) / (k_ms * 1e-3) / 1e9
+    cpu_g, kind, cores, text = cpu_reference_gcups(min(n, 12000), seed)
+    return {
+        "metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": env.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "s16x2" if info["lanes"] == 16 else "s32", "data": "synthetic",
+        "config": {"workload": name, "description": desc, "pairs_per_gpu": pairs,
+                   "l2": "flushed between timed steps (256 MiB write)", "kernel": info,
+                   "score_checked_against": "oracle, every pair" if name == "cfg1" else ("pinned golden, every step" if want[0] is not None else None),
+                   "score_checked_against_golden": want[0] is not None},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(n + m) * pairs, "d2h_bytes_per_step": 40 * pairs,
+                "call": "SmithWatermanScoreCUDA(host bytes) via libswb200.so C ABI, wall clock"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                     "frac": round(achieved / peak, 4), "traffic": ncu_traffic(name),
+                     "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); traffic = DRAM bytes per launch "
+                             f"from the committed ncu capture, algorithmic input is {(n + m) // 4} bytes, "
+                             f"the boundary rows of the bands live in L2; peak = 148 SM x {f_mhz} MHz x "
+                             f"L={DPX_LANE_INSTR_PER_CLK_PER_SM:.0f} DPX lane-instr/clk/SM (measured, bench/intpeak.cu) x V={vwidth} / 7 "
+                             "instr per cell vector (SURVEY.md 8d); not an HBM- or tensor-bound kernel"},
+        "cpu_baseline": {"value": round(cpu_g, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
+    }
 
 
-def run_batch(args, torch, dist, api, world, rank, local):
-    """Many independent pairs per GPU (BASELINE config 4), no communication on the data path (weak scaling)."""
-    import oracle_lib as O
-    npairs, rl, wl = BATCH_WORKLOADS[args.workload]
-    banded = args.workload in BANDED
-    g = torch.Generator(device="cuda"); g.manual_seed(4000 + rank)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
-
-    def rand_acgt(rows, cols):
-        out = torch.empty((rows, cols), dtype=torch.uint8, device="cuda")
-        for r0 in range(0, rows, 16384):           # chunked: the int64 index tensor of lut[] is 8x the output
-            r1 = min(rows, r0 + 16384)
-            out[r0:r1] = lut[torch.randint(0, 4, (r1 - r0, cols), generator=g, device="cuda", dtype=torch.uint8).long()]
-        return out
-
-    wins = rand_acgt(npairs, wl)
-    if banded:
-        # long reads: seq1 = seq2 with ~10% substitutions (every 4th pair unrelated), so the optimum stays in the band
-        reads = wins.clone()
-        for r0 in range(0, npairs, 16384):
-            r1 = min(npairs, r0 + 16384)
-            sub = torch.rand((r1 - r0, rl), generator=g, device="cuda") < 0.10
-            unrelated = (torch.arange(r0, r1, device="cuda") % 4 == 0)[:, None]
-            noise = lut[torch.randint(0, 4, (r1 - r0, rl), generator=g, device="cuda", dtype=torch.uint8).long()]
-            reads[r0:r1] = torch.where(sub | unrelated, noise, reads[r0:r1])
-    else:
-        # reads: even pairs = a window substring with ~5% substitutions, odd pairs = random
-        offs = torch.randint(0, wl - rl, (npairs,), generator=g, device="cuda")
-        idx = offs[:, None] + torch.arange(rl, device="cuda")[None, :]
-        reads = torch.gather(wins, 1, idx)
-        noise = rand_acgt(npairs, rl)
-        sub = torch.rand((npairs, rl), generator=g, device="cuda") < 0.05
-        odd = (torch.arange(npairs, device="cuda") % 2 == 1)[:, None]
-        reads = torch.where(sub | odd, noise, reads).contiguous()
-    wins = wins.contiguous()
-    off1 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * rl).contiguous()
-    off2 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * wl).contiguous()
-    len1 = torch.full((npairs,), rl, dtype=torch.int32, device="cuda")
-    len2 = torch.full((npairs,), wl, dtype=torch.int32, device="cuda")
-    scores = torch.zeros(npairs, dtype=torch.int32, device="cuda")
-    ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
-    lo, hi = -32, 31
-    if banded:     # exact in-band cell count of one n x m pair (i = row in seq2, j = column in seq1)
-        i = np.arange(1, wl + 1)
-        per_pair = int(np.maximum(0, np.minimum(rl, i + hi) - np.maximum(1, i + lo) + 1).sum())
-    else:
-        per_pair = rl * wl
-    cells = float(npairs) * per_pair
-    batch = api.PackedBatch(ctx, reads.data_ptr(), off1.data_ptr(), len1.data_ptr(), wins.data_ptr(), off2.data_ptr(),
-                            len2.data_ptr(), npairs, rl, wl, int(cells), stream=stream.cuda_stream, keep_order=banded)
-
-    def run_kernel():
-        if banded:
-            batch.score_banded(scores.data_ptr(), lo, hi, stream=stream.cuda_stream, no_linear=args.no_linear)
-        else:
-            batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
-
-    for _ in range(max(args.warmup, 3)):
-        run_kernel()
-    # parity on a seeded sample of pairs against the oracle, every run
-    sample = torch.arange(0, npairs, max(1, npairs // 512), device="cuda")[:512]
-    r_h, w_h, s_h = reads[sample].cpu().numpy(), wins[sample].cpu().numpy(), scores[sample].cpu().numpy()
-    if banded:
-        r_h, w_h, s_h = r_h[:64], w_h[:64], s_h[:64]
-        want = O.gotoh_banded_batch(list(r_h), list(w_h), lo, hi)
-    else:
-        want = O.gotoh_batch(list(r_h), list(w_h))
-    if want.tolist() != s_h.tolist():
-        raise SystemExit("bench.py: batch scores differ from the oracle on the sample")
-    checksum = int(scores.to(torch.int64).sum())
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    kms = []
-    for _ in range(args.steps):      # 0.6-1.7 GB of packed input per pass: far larger than L2, no flush needed
-        run_kernel()
-        kms.append(ctx.last_run()["engine_ms"])
-    e1.record(stream)
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    dev_ms = e0.elapsed_time(e1)
-    assert int(scores.to(torch.int64).sum()) == checksum
-    # end to end from host bytes on a slice of the batch (H2D of sequences, pack, kernel, D2H of the scores)
-    ne = min(npairs, 20000 if banded else 200000)
-    # pinned host buffers, as the bench contract asks: the library then copies at PCIe speed and overlaps the copy
-    # of chunk k+1 with packing and scoring chunk k
-    r_e, w_e = reads[:ne].cpu().pin_memory().numpy().reshape(-1), wins[:ne].cpu().pin_memory().numpy().reshape(-1)
-    o1, o2 = off1[:ne].cpu().pin_memory().numpy(), off2[:ne].cpu().pin_memory().numpy()
-    l1, l2 = len1[:ne].cpu().pin_memory().numpy(), len2[:ne].cpu().pin_memory().numpy()
-
-    def host_call():
-        if banded:
-            return api.score_banded_batch_flat(r_e, o1, l1, w_e, o2, l2, lo, hi)
-        return api.score_batch_flat(r_e, o1, l1, w_e, o2, l2)
-
-    host_call()
-    t1 = time.perf_counter()
-    out = host_call()
-    e2e_s = time.perf_counter() - t1
-    assert out.tolist() == scores[:ne].cpu().numpy().tolist()
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        info = ctx.last_run()
-        value = cells * world * args.steps / (dev_ms * 1e-3) / 1e9
-        e2e_val = float(ne) * per_pair * world / (e2e_ms * 1e-3) / 1e9
-        f_mhz = clocks["sm_mhz"] or 1965
-        peak = N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * 2 / INSTR_PER_CELL_VECTOR / 1e9
-        achieved = cells / (float(np.mean(kms)) * 1e-3) / 1e9
-        # reference CPU on a sample: one reference call per pair, spread over the host cores
-        nb = 2000
-        t0 = time.perf_counter()
-        if banded:
-            cores = O.oracle().oracle_max_threads()
-            O.gotoh_banded_batch(list(r_h) * 4, list(w_h) * 4, lo, hi)
-            nb, kind = 4 * len(r_h), "port"
-        elif O.ref_available():
-            import ctypes as C
-            f1, o1s, l1s = O._batch_args(list(r_h) * 4)
-            f2, o2s, l2s = O._batch_args(list(w_h) * 4)
-            nb = len(l1s)
-            outb = np.zeros(nb, dtype=np.int32)
-            cores = os.cpu_count() or 1
-            O.ref().ref_batch(2, O._ptr(f1), o1s.ctypes.data_as(C.POINTER(C.c_longlong)), l1s.ctypes.data_as(C.POINTER(C.c_int)),
-                              O._ptr(f2), o2s.ctypes.data_as(C.POINTER(C.c_longlong)), l2s.ctypes.data_as(C.POINTER(C.c_int)),
-                              nb, cores, outb.ctypes.data_as(C.POINTER(C.c_int)))
-            kind = "reference"
-        else:
-            cores = O.oracle().oracle_max_threads()
-            O.gotoh_batch(list(r_h) * 4, list(w_h) * 4)
-            nb, kind = 4 * len(r_h), "port"
-        cpu_g = nb * (rl * wl if not banded else per_pair) / (time.perf_counter() - t0) / 1e9
-        line = {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
-                "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3], "pairs_per_gpu": npairs,
-                           "l2": "inputs (1.7 GB packed per GPU) larger than L2", "kernel": info,
-                           "sample_checked_against_oracle": int(len(s_h))},
-                "clocks": clocks, "gpu_launches": args.steps,
-                "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(ne * (rl + wl + 24)),
-                        "d2h_bytes_per_step": int(4 * ne), "call": f"swb200_score{'_banded' if banded else ''}_batch(host bytes) on {ne} pairs per GPU, wall clock"},
-                "roofline": {"bound": "int_alu", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                             "frac": round(achieved / peak, 4), "traffic": None,
-                             "note": f"batch kernel, one GPU; peak = 148 SM x {f_mhz} MHz x L=64 x V=2 / 7"},
-                "cpu_baseline": {"value": round(cpu_g, 3), "unit": "GCUPS", "cores": cores, "kind": kind,
-                                 "sample": (f"{nb} pairs of the batch, oracle_gotoh_banded per pair over {cores} threads (the reference has no banded mode)"
-                                            if banded else
-                                            f"{nb} pairs of the batch, one ParallelLazySmith_threads call per pair, pairs spread over {cores} host threads")}}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    batch.close()
-
-
-def run_ring(args, torch, dist, api, world, rank, local):
+def ring_record(env, args, name, steps, warmup):
     """One long pair over all GPUs (strong scaling).  Every rank holds both sequences; the DP bands are dealt
     cyclically to the warps of all GPUs and the boundary stream crosses GPUs inside the kernel."""
+    torch, dist = env.torch, env.dist
     from concurrentproject_b200.ring import DistributedRingAligner
-    if world == 1:
-        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29591", rank=0, world_size=1,
-                                device_id=torch.device("cuda", local))
-    n, m, seed, desc = WORKLOADS[args.workload]
+    env.need_group()
+    n, m, seed, desc = RING_WORKLOADS[name]
+    want = golden_score(name)
     a_h = rng.random_acgt(seed, 0, n)
     b_h = rng.random_acgt(seed, 1, m)
     a_d = torch.from_numpy(a_h.copy()).cuda()
     b_d = torch.from_numpy(b_h.copy()).cuda()
-    al = DistributedRingAligner(local, min(n, m))
-    stream = torch.cuda.current_stream()
+    al = DistributedRingAligner(env.local, min(n, m))
+    stream = env.stream
     lanes = 32 if args.lanes32 else 0             # default: library policy (re-based 16-bit lanes for long pairs)
+    two_sided = -1 if args.one_sided else 0
     scores = []
-    for _ in range(max(args.warmup, 1)):
-        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
+    for _ in range(max(warmup, 1)):
+        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream, two_sided=two_sided))
     dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(env.local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     kms = []
-    for _ in range(args.steps):
-        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
+    for _ in range(steps):
+        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream, two_sided=two_sided))
         kms.append(al.last_run()["engine_ms"])
     e1.record(stream)
     torch.cuda.synchronize()
@@ -477,40 +369,205 @@ def run_ring(args, torch, dist, api, world, rank, local):
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         a_d.copy_(a_p, non_blocking=True)
         b_d.copy_(b_p, non_blocking=True)
-        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream))
+        scores.append(al.score(a_d.data_ptr(), n, b_d.data_ptr(), m, lanes=lanes, stream=stream.cuda_stream, two_sided=two_sided))
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e0.elapsed_time(e1), e2e_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
-    assert len(set(scores)) == 1, scores
-    cells = float(n) * float(m)
-    if rank == 0:
-        info = al.last_run()
-        value = cells * args.steps / (ms * 1e-3) / 1e9
-        f_mhz = clocks["sm_mhz"] or 1965
-        vwidth = 2 if info["lanes"] == 16 else 1
-        peak = world * N_SM * f_mhz * 1e6 * DPX_LANE_INSTR_PER_CLK_PER_SM * vwidth / INSTR_PER_CELL_VECTOR / 1e9
-        line = {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 1), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None,
-                "dtype": ("s16x2 re-based" if info.get("rebased") else "s16x2") if info["lanes"] == 16 else "s32", "data": "synthetic",
-                "config": {"workload": args.workload, "description": desc, "l2": "working set is registers; boundary rings stream through L2",
-                           "kernel": info, "score": scores[-1]},
-                "clocks": clocks, "gpu_launches": 3 * args.steps,
-                "e2e": {"value": round(cells * args.steps / (e2e_ms * 1e-3) / 1e9, 1), "unit": "GCUPS",
-                        "h2d_bytes_per_step": int(n + m) * world, "d2h_bytes_per_step": 16 * world,
-                        "call": "DistributedRingAligner.score after copying both sequences from pinned host memory on every rank, wall clock, max over ranks"},
-                "roofline": {"bound": "int_alu", "achieved": round(value, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                             "frac": round(value / peak, 4), "traffic": None,
-                             "note": f"whole ring of {world} GPU(s); peak = {world} x 148 SM x {f_mhz} MHz x L=64 x V={vwidth} / 7"}}
-        print(json.dumps(line), flush=True)
-    dist.barrier()
+    ms, e2e_ms, k_ms = env.max_over_ranks([e0.elapsed_time(e1), e2e_ms, float(np.mean(kms))])
+    if len(set(scores)) != 1:
+        raise SystemExit(f"bench.py: ring scores differ between steps: {scores}")
+    if want is not None and scores[-1] != want:
+        raise SystemExit(f"bench.py: ring score {scores[-1]} != pinned {want}")
+    info = al.last_run()
     al.close()
-    dist.destroy_process_group()
+    if env.rank != 0:
+        return None
+    cells = float(n) * float(m)
+    value = cells * steps / (ms * 1e-3) / 1e9
+    f_mhz = clocks["sm_mhz"] or 1965
+    vwidth = 2 if info["lanes"] == 16 else 1
+    peak = peak_gcups(f_mhz, vwidth, env.world)
+    return {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": env.world, "steps": steps,
+            "warmup": max(warmup, 1), "ms_per_step": round(ms / steps, 3), "kernel_ms_max_over_ranks": round(k_ms, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": ("s16x2 re-based" if info.get("rebased") else "s16x2") if info["lanes"] == 16 else "s32", "data": "synthetic",
+            "config": {"workload": name, "description": desc, "l2": "working set is registers; boundary rings stream through L2",
+                       "kernel": info, "score": scores[-1], "score_checked_against_golden": want is not None},
+            "clocks": clocks, "gpu_launches": (info["engine_launches"] + info["aux_launches"]) * steps,
+            "e2e": {"value": round(cells * steps / (e2e_ms * 1e-3) / 1e9, 1), "unit": "GCUPS",
+                    "h2d_bytes_per_step": int(n + m) * env.world, "d2h_bytes_per_step": 16 * env.world,
+                    "call": "DistributedRingAligner.score after copying both sequences from pinned host memory on every rank, wall clock, max over ranks"},
+            "roofline": {"bound": "int_alu", "achieved": round(value, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                         "frac": round(value / peak, 4), "traffic": None,
+                         "note": f"whole ring of {env.world} GPU(s); peak = {env.world} x 148 SM x {f_mhz} MHz x L=64 x V={vwidth} / 7"}}
+
+
+def batch_record(env, args, name, steps, warmup):
+    """A fixed total batch cut into contiguous ranges of pairs, one per GPU (strong scaling, no communication on the
+    data path).  Inputs come from the seeded device generator by GLOBAL pair id, so every GPU count scores the very
+    same pairs; a sample is regenerated on the host (rng.read_pair / rng.long_pair) and checked against the oracle."""
+    torch, api = env.torch, env.api
+    import oracle_lib as O
+    total, l1, l2, seed, banded, desc = BATCH_WORKLOADS[name]
+    per = (total + env.world - 1) // env.world
+    k0 = min(total, env.rank * per)
+    npairs = min(total, k0 + per) - k0
+    stream = env.stream
+    seq1 = torch.empty((max(npairs, 1), l1), dtype=torch.uint8, device="cuda")
+    seq2 = torch.empty((max(npairs, 1), l2), dtype=torch.uint8, device="cuda")
+    if banded:
+        api.gen_long_pairs_device(env.local, seed, k0, npairs, l1, seq1.data_ptr(), seq2.data_ptr(), stream.cuda_stream)
+    else:
+        api.gen_read_pairs_device(env.local, seed, k0, npairs, l1, l2, seq1.data_ptr(), seq2.data_ptr(), stream.cuda_stream)
+    off1 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * l1).contiguous()
+    off2 = (torch.arange(npairs, device="cuda", dtype=torch.int64) * l2).contiguous()
+    len1 = torch.full((npairs,), l1, dtype=torch.int32, device="cuda")
+    len2 = torch.full((npairs,), l2, dtype=torch.int32, device="cuda")
+    scores = torch.zeros(npairs, dtype=torch.int32, device="cuda")
+    ctx = api.Context(env.local)
+    lo, hi = -32, 31
+    if banded:     # exact in-band cell count of one n x m pair (i = row in seq2, j = column in seq1)
+        i = np.arange(1, l2 + 1)
+        per_pair = int(np.maximum(0, np.minimum(l1, i + hi) - np.maximum(1, i + lo) + 1).sum())
+    else:
+        per_pair = l1 * l2
+    cells_total = float(total) * per_pair
+    batch = api.PackedBatch(ctx, seq1.data_ptr(), off1.data_ptr(), len1.data_ptr(), seq2.data_ptr(), off2.data_ptr(),
+                            len2.data_ptr(), npairs, l1, l2, int(float(npairs) * per_pair), stream=stream.cuda_stream, keep_order=banded)
+
+    def run_kernel():
+        if banded:
+            batch.score_banded(scores.data_ptr(), lo, hi, stream=stream.cuda_stream, no_linear=args.no_linear)
+        else:
+            batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
+
+    for _ in range(max(warmup, 3)):
+        run_kernel()
+    # parity on a seeded sample of pairs, regenerated on the HOST from their global ids, against the oracle
+    want_sample = (1000 if banded else 10000) // env.world
+    idx = np.unique(np.linspace(0, max(npairs - 1, 0), num=min(want_sample, npairs)).astype(np.int64)) if npairs else np.zeros(0, dtype=np.int64)
+    gen = (lambda k: rng.long_pair(seed, k, l1)) if banded else (lambda k: rng.read_pair(seed, k, l1, l2))
+    hp = [gen(int(k0 + p)) for p in idx]
+    got = scores[torch.from_numpy(idx).cuda()].cpu().numpy() if len(idx) else np.zeros(0, dtype=np.int32)
+    if len(idx):
+        want = O.gotoh_banded_batch([a for a, _ in hp], [b for _, b in hp], lo, hi) if banded else O.gotoh_batch([a for a, _ in hp], [b for _, b in hp])
+        if want.tolist() != got.tolist():
+            bad = int(np.argmax(want != got))
+            raise SystemExit(f"bench.py: batch scores differ from the oracle on the sample (pair {int(k0 + idx[bad])}: {int(got[bad])} != {int(want[bad])})")
+
+    def checksum():   # 64-bit, position dependent, over ALL scores of this rank (global pair ids)
+        ids = torch.arange(k0, k0 + npairs, device="cuda", dtype=torch.int64)
+        s64 = scores.to(torch.int64)
+        return int(s64.sum()), int((s64 * (ids % 1000003 + 1)).sum())       # < 2^63 for every workload here
+
+    chk = checksum()
+    env.barrier()
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kms = []
+    for _ in range(steps):      # packed inputs per pass are far larger than L2: no flush needed
+        run_kernel()
+        kms.append(ctx.last_run()["engine_ms"])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    if checksum() != chk:
+        raise SystemExit("bench.py: batch checksum changed between passes")
+    # end to end from HOST bytes: H2D of the sequences, pack, kernel, D2H of the scores, through the C ABI host call
+    ne = min(npairs, 2500000 if not banded else 250000)
+    r_e, w_e = seq1[:ne].cpu().pin_memory().numpy().reshape(-1), seq2[:ne].cpu().pin_memory().numpy().reshape(-1)
+    o1, o2 = off1[:ne].cpu().pin_memory().numpy(), off2[:ne].cpu().pin_memory().numpy()
+    ln1, ln2 = len1[:ne].cpu().pin_memory().numpy(), len2[:ne].cpu().pin_memory().numpy()
+    del seq1, seq2
+    torch.cuda.empty_cache()
+
+    def host_call():
+        if banded:
+            return api.score_banded_batch_flat(r_e, o1, ln1, w_e, o2, ln2, lo, hi)
+        return api.score_batch_flat(r_e, o1, ln1, w_e, o2, ln2)
+
+    out = host_call() if ne else np.zeros(0, dtype=np.int32)
+    env.barrier()
+    t1 = time.perf_counter()
+    out = host_call() if ne else out
+    e2e_s = time.perf_counter() - t1
+    if out.tolist() != scores[:ne].cpu().numpy().tolist():
+        raise SystemExit("bench.py: host batch call disagrees with the device-resident pass")
+    dev_ms, e2e_ms, k_ms = env.max_over_ranks([dev_ms, e2e_s * 1e3, float(np.mean(kms))])
+    sum_scores, weighted, n_checked, ne_total = env.sum_over_ranks_i64([chk[0], chk[1], len(idx), ne])
+    info = ctx.last_run()
+    batch.close()
+    if env.rank != 0:
+        return None
+    value = cells_total * steps / (dev_ms * 1e-3) / 1e9
+    e2e_val = float(ne_total) * per_pair / (e2e_ms * 1e-3) / 1e9
+    f_mhz = clocks["sm_mhz"] or 1965
+    peak = peak_gcups(f_mhz, 2, env.world)
+    # reference CPU on a sample: one reference call per pair, spread over the host cores
+    rs, ws = [a for a, _ in hp][:500 if banded else 4000], [b for _, b in hp][:500 if banded else 4000]
+    t0 = time.perf_counter()
+    if banded:
+        cores, kind = O.oracle().oracle_max_threads(), "port"
+        O.gotoh_banded_batch(rs, ws, lo, hi)
+    elif O.ref_available():
+        import ctypes as C
+        f1, o1s, l1s = O._batch_args(rs)
+        f2, o2s, l2s = O._batch_args(ws)
+        outb = np.zeros(len(rs), dtype=np.int32)
+        cores, kind = os.cpu_count() or 1, "reference"
+        O.ref().ref_batch(2, O._ptr(f1), o1s.ctypes.data_as(C.POINTER(C.c_longlong)), l1s.ctypes.data_as(C.POINTER(C.c_int)),
+                          O._ptr(f2), o2s.ctypes.data_as(C.POINTER(C.c_longlong)), l2s.ctypes.data_as(C.POINTER(C.c_int)),
+                          len(rs), cores, outb.ctypes.data_as(C.POINTER(C.c_int)))
+    else:
+        cores, kind = O.oracle().oracle_max_threads(), "port"
+        O.gotoh_batch(rs, ws)
+    cpu_g = len(rs) * per_pair / (time.perf_counter() - t0) / 1e9
+    return {"metric": METRIC, "value": round(value, 1), "unit": "GCUPS", "n_gpus": env.world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": round(dev_ms / steps, 3), "kernel_ms_max_over_ranks": round(k_ms, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s16x2",
+            "data": "synthetic (seeded device generator, csrc/swb_gen.cu = concurrentproject_b200/rng.py)",
+            "config": {"workload": name, "description": desc, "pairs_total": total, "pairs_per_gpu": per,
+                       "l2": "packed inputs per pass are far larger than L2", "kernel": info,
+                       "sample_checked_against_oracle": n_checked,
+                       "checksum": {"sum_of_scores": sum_scores, "weighted": weighted,
+                                    "note": "over ALL pairs, by global pair id: identical for every GPU count"}},
+            "clocks": clocks, "gpu_launches": steps,
+            "e2e": {"value": round(e2e_val, 1), "unit": "GCUPS", "h2d_bytes_per_step": int(ne * (l1 + l2 + 24)) * env.world,
+                    "d2h_bytes_per_step": int(4 * ne) * env.world,
+                    "call": f"swb200_score{'_banded' if banded else ''}_batch(pinned host bytes) on {ne} pairs per GPU ({ne_total} in all), wall clock, max over ranks"},
+            "roofline": {"bound": "int_alu", "achieved": round(value, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                         "frac": round(value / peak, 4), "traffic": None,
+                         "note": f"batch kernel on {env.world} GPU(s); peak = {env.world} x 148 SM x {f_mhz} MHz x L=64 x V=2 / 7"},
+            "cpu_baseline": {"value": round(cpu_g, 3), "unit": "GCUPS", "cores": cores, "kind": kind,
+                             "sample": (f"{len(rs)} pairs of the batch, oracle_gotoh_banded per pair over {cores} threads (the reference has no banded mode)"
+                                        if banded else
+                                        f"{len(rs)} pairs of the batch, one ParallelLazySmith_threads call per pair, pairs spread over {cores} host threads")}}
+
+
+def run_ours(args):
+    env = Env()
+    name = args.workload
+    if name in RING_WORKLOADS:
+        line = ring_record(env, args, name, args.steps, args.warmup)
+    elif name in BATCH_WORKLOADS:
+        line = batch_record(env, args, name, args.steps, args.warmup)
+    else:
+        line = pair_record(env, args, name)
+        if name == "cfg2" and not args.no_extra:
+            # the two multi-GPU designs of BASELINE configs 3 and 4 on the same N GPUs, in the same run
+            ring = ring_record(env, args, "cfg3", 2, 1)
+            batch = batch_record(env, args, "cfg4", 3, 3)
+            if env.rank == 0:
+                line["ring"] = ring
+                line["batch"] = batch
+    if env.rank == 0:
+        print(json.dumps(line), flush=True)
+    env.close()
 
 
 def main():
@@ -519,8 +576,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=ALL_WORKLOADS)
+    ap.add_argument("--no-extra", action="store_true", help="headline only: skip the cfg3 ring and cfg4 batch sub-records")
     ap.add_argument("--lanes32", action="store_true", help="ring workloads: force the 32-bit kernel")
+    ap.add_argument("--one-sided", action="store_true", help="ring workloads: never sweep from both ends")
     ap.add_argument("--no-linear", action="store_true",
                     help="keep the general affine kernel although GAP_INIT == GAP_EXT (default: use the exact E/F-free kernel)")
     args = ap.parse_args()

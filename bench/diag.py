@@ -87,8 +87,8 @@ if "cfgsweep" in what:
                         rec = {"kind": "cfgsweep", "n": nn, "mode": mode, "R": R, "config": config, "pure": pure, "ms": round(best, 4),
                                "bands": info["bands"], "warps": info["warps"], "rebased": info["rebased"], "ok": bool(pure or s == want)}
                         if pure:
-                            slack = {1: 1, 5: 1, 4: 2, 6: 2}.get(config, 0)
-                            nsteps = (nn + 31 * (2 + slack) + 1 + 31) // 32 * 32
+                            slack, hs = {1: (1, 0), 4: (1, 1)}.get(config, (0, 0))
+                            nsteps = (nn + 31 * (2 + slack + hs) + 1 + hs + 255) // 256 * 256
                             rounds = -(-info["bands"] // info["warps"])
                             rec["cyc_per_step"] = round(best * 1e-3 * MHZ * 1e6 / (nsteps * rounds), 2)
                         else:

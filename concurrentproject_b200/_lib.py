@@ -71,6 +71,11 @@ EXPORTS = {
                                    C.POINTER(C.c_int)], C.c_int),
     "swb200_batch_score_banded": ([C.c_void_p, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(Options), C.c_void_p,
                                    C.c_void_p], C.c_int),
+    "swb200_gen_random_device": ([C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
+    "swb200_gen_read_pairs_device": ([C.c_int, C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p], C.c_int),
+    "swb200_gen_long_pairs_device": ([C.c_int, C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p], C.c_int),
     "swb200_ring_create": ([C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_void_p), C.c_char * 64], C.c_int),
     "swb200_ring_connect": ([C.c_void_p, C.c_char * 64], C.c_int),
     "swb200_ring_connect_local": ([C.c_void_p, C.c_void_p], C.c_int),

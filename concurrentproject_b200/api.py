@@ -281,3 +281,39 @@ class PackedBatch:
         if self.handle:
             _lib.load().swb200_batch_free(self.handle)
             self.handle = C.c_void_p()
+
+
+# ---- seeded synthetic inputs generated in HBM (swb200_gen_*_device; host mirror: concurrentproject_b200/rng.py) ----
+def gen_random_device(device: int, seed: int, stream_id: int, length: int, d_out: int, stream: int = 0) -> None:
+    rc = _lib.load().swb200_gen_random_device(device, seed, stream_id, length, C.c_void_p(d_out), C.c_void_p(stream))
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_random_device")
+
+
+def gen_read_pairs_device(device: int, seed: int, first_pair: int, npairs: int, read_len: int, window_len: int, d_reads: int,
+                          d_windows: int, stream: int = 0) -> None:
+    """BASELINE config 4 inputs for pairs first_pair .. first_pair+npairs-1 (rng.read_pair per pair)."""
+    rc = _lib.load().swb200_gen_read_pairs_device(device, seed, first_pair, npairs, read_len, window_len, C.c_void_p(d_reads),
+                                                  C.c_void_p(d_windows), C.c_void_p(stream))
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_read_pairs_device")
+
+
+def gen_long_pairs_device(device: int, seed: int, first_pair: int, npairs: int, length: int, d_seq1: int, d_seq2: int,
+                          stream: int = 0) -> None:
+    """BASELINE config 5 inputs for pairs first_pair .. first_pair+npairs-1 (rng.long_pair per pair)."""
+    rc = _lib.load().swb200_gen_long_pairs_device(device, seed, first_pair, npairs, length, C.c_void_p(d_seq1), C.c_void_p(d_seq2),
+                                                  C.c_void_p(stream))
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_long_pairs_device")
+
+
+def set_devices(count: int) -> None:
+    """Host-buffer calls (score, score_batch, the four legacy names) use devices 0..count-1 (swb200_set_devices)."""
+    rc = _lib.load().swb200_set_devices(count)
+    if rc != 0:
+        raise SwbError(rc, "swb200_set_devices")
+
+
+def get_devices() -> int:
+    return int(_lib.load().swb200_get_devices())

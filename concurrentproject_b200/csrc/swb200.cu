@@ -387,15 +387,16 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const long long NB = (LQ + rpb - 1) / rpb;
   const int wpc = swb::config_wpc(config), slack = swb::config_slack(config);
   const long long W = (long long)sms * wpc;
-  const int skew = swb::mode_is_s32(mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  static const double kPerRowShort[10] = {13.2, 7.5, 12.0, 15.6, 9.8, 14.0, 14.0, 16.0, 14.5, 16.5};
+  const int skew = swb::config_skew(config, mode);
+  static const double kPerRowShort[10] = {13.2, 7.0, 12.0, 15.6, 9.8, 14.0, 14.0, 16.0, 14.5, 16.5};
   static const double kPerRowLong[10] = {14.0, 10.0, 12.5, 15.0, 11.0, 14.5, 14.5, 16.5, 15.0, 17.0};
   const double per_row = (config == 2 ? kPerRowLong : kPerRowShort)[mode];
-  double cyc_step = per_row * R + (config == 2 ? 39.0 : 30.0);
-  if (config != 2) cyc_step = std::max(cyc_step, 55.0);      // latency floor of a step with one warp per scheduler
+  double cyc_step = per_row * R + (config == 2 ? 39.0 : 31.0);
+  if (config != 2) cyc_step = std::max(cyc_step, 48.0);      // latency floor of a step with one warp per scheduler (r02_diag: R=2 -> 48.7)
   if (config == 2) cyc_step *= 1.5;
   if (config == 3) cyc_step += std::max(0.0, 30.0 - ((mode == 1 || mode == 4) ? 4.0 : 6.0) * R);   // exposed SHFL latency
-  const double lag = skew + 48 + 60;        // 32 steps of poll granularity + 16 of speculative look-ahead + visibility
+  const double lag = skew + 48 + 26;        // 32 steps of poll granularity + 16 of speculative look-ahead + visibility
+                                            // (measured with %globaltimer stamps per band: 168 steps at skew 94, profiles/r02_diag_baseline.txt)
   if (two_sided) {            // each half has half the bands and half the warps
     const long long NBh = (NB + 1) / 2, Wh = std::max<long long>(W / 2, 1);
     const long long b = NBh - 1, w = b % Wh, r = b / Wh;
@@ -406,10 +407,6 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   const double start = std::max((double)w * lag + (double)r * (double)(LT + skew), (double)b * lag);
   return (start + (double)(LT + skew)) * cyc_step;
 }
-
-struct Plan;
-const void* kernel_for(const Plan& pl);
-constexpr int kAutoConfigs = 3;      // launch configs the planner chooses from by itself
 
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms,
                bool allow_two_sided = false) {
@@ -426,11 +423,11 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   if (lanes == 37) pl.mode = 9;
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
-    if (o.config ? o.config != ci : ci > kAutoConfigs) continue;       // the rest: only when asked for
+    if (o.config && o.config != ci) continue;
+    if (ci > 3 && (swb::mode_is_s32(pl.mode) || !o.config)) continue;      // config 4: 16-bit lanes, and (until fitted) only on request
     for (int ri = 0; ri < swb::kNumRowChoices; ++ri) {
       const int R = swb::kRowChoices[ri];
       if (o.rows && o.rows != R) continue;
-      { Plan probe = pl; probe.R = R; probe.config = ci; if (!kernel_for(probe)) continue; }
       const double e = estimate(LQ, LT, pl.mode, R, ci, sms);
       if (e < best && !(o.two_sided > 0 && pl.two_sided)) { best = e; pl.R = R; pl.config = ci; pl.two_sided = false; }
       // two-sided: packed 16-bit lanes (plain or re-based), at least 4 bands per half
@@ -514,8 +511,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const int warps = (int)ctas * wpc;
   const int split = ts ? warps / 2 : 0;
 
-  const int skew = swb::mode_is_s32(pl.mode) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const int align = (pl.mode == 3 || pl.mode == 4) ? swb::kRebaseBlock : swb::kChunk;
+  const int skew = swb::config_skew(pl.config, pl.mode);
+  const int align = swb::mode_is_s32(pl.mode) ? swb::kChunk : swb::kBlock;     // steps per band: whole chunks / whole blocks
   const long long nsteps = ((LT + skew + align - 1) / align) * align;
   const int ext_shift = std::max(4, log2_ceil(nsteps + swb::kChunk));
   const long long ext_len = 1LL << ext_shift;

@@ -38,12 +38,6 @@ SWB_HD constexpr int step_unroll(double instr_per_row, int rows, int big) { retu
 #define SWB_STEP_UNROLL32 8
 #endif
 constexpr int kStepUnroll32 = SWB_STEP_UNROLL32;   // 32-bit engine
-// Measurement builds only (bench/knock.sh): SWB_KNOCK is a bit mask of step-loop components to leave out -- scores are
-// WRONG, the time difference is what the component costs.  1 boundary store, 2 inbox load + select, 4 table load,
-// 8 shuffle, 16 running best, 32 chunk prologue work (table fill, polls).
-#ifndef SWB_KNOCK
-#define SWB_KNOCK 0
-#endif
 constexpr int kChunk = 32;     // steps between boundary polls / table refills
 constexpr int kTabRing = 256;  // per-warp ring of substitution tables (one per T position), kept twice
 constexpr int kInbox = 64;     // per-warp ring of validated top-boundary values
@@ -164,6 +158,38 @@ SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned lo
   }
 }
 
+// Rare path of the chunk prologue, kept out of line so that the common path is straight-line code: the boundary
+// entry (and, re-based lanes, the producer's base entry) this lane needs has not arrived yet.  Polls until every
+// lane of the warp has what it needs (warp-uniform exit: a per-lane spin loop leaves the warp diverged, and every
+// later __shfl_sync then takes the divergent slow path -- measured 5x slower steps on B200), or until the wait
+// budget is spent; then STATUS_SPIN_TIMEOUT is set, the caller stops expecting entries and the host reports
+// SWB200_ERR_TIMEOUT.
+template <class Ctx>
+__host__ __device__ __noinline__ long long poll_boundary(const EngineParams& P, const Ctx& w, bool need, const uint2* slot,
+                                                         uint32_t want, const uint2* bslot, uint32_t bwant, bool with_base,
+                                                         long long budget) {
+  // Everything goes in and out BY VALUE (the remaining budget is the result, -1 = gave up): a reference parameter
+  // would force the caller's registers into local memory on the hot path.
+  for (;;) {
+    bool ok = true;
+    uint2 e = make_uint2(0u, 0u), be = make_uint2(0u, 0u);
+    if (need) {
+      e = ld_entry(slot);
+      ok = e.y == want;
+      if (with_base) { be = ld_entry(bslot); ok = ok && be.y == bwant; }
+    }
+    if (w.all(ok)) return budget < 0 ? 0 : budget;
+    bool give_up = --budget < 0;
+    if ((budget & 255) == 0) give_up = give_up || (ld_flag(P.result + 1) & STATUS_SPIN_TIMEOUT);
+    if (w.any(give_up)) {
+      if (!ok) record_timeout(P, 1, (long long)want, (long long)e.y, (long long)e.x, budget);
+      atomic_or_i32(P.result + 1, STATUS_SPIN_TIMEOUT);
+      return -1;
+    }
+    spin_pause();
+  }
+}
+
 // =================================================================================================
 //  Packed 16-bit engine.  MODE 0: affine gaps.  MODE 1: gap_init == gap_ext (E/F eliminated).
 //  SLACK 1: a shuffled boundary value is consumed one step after it was sent (hides SHFL latency
@@ -174,19 +200,32 @@ SWB_HD void wait_progress(const EngineParams& P, const Ctx& w, const unsigned lo
 //  so they always fit 16 bits around a common base; the zero floor becomes max(.., -base); every 256
 //  steps the warp re-centres (adds a constant to all its registers) and publishes its base next to
 //  the boundary entries so the band below can translate what it receives.
+//
+//  Loop structure (round 2).  With one warp per scheduler nothing hides a branch: ncu's source page showed the
+//  32-step chunk prologue of round 1 at ~500 cycles (a quarter of the sweep) although it issues only ~150
+//  instructions -- a dozen small branches at 15-30 cycles each (predicate -> branch latency, refetch after a taken
+//  branch), three clock reads of the profiling hook, 64-bit index arithmetic.  So: blocks of 256 steps carry
+//  everything that happens less often than once per chunk (re-basing, progress word, ring back-pressure); the chunk
+//  prologue is straight-line code with ONE vote and one never-taken branch to the out-of-line poll loop; the
+//  profiling hook is compiled in only with -DSWB_ENABLE_PROF (bench/diag.py builds).
 // =================================================================================================
 SWB_HD int hi_half_max(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a > b ? a : b; }
 SWB_HD int lo_half_min(uint32_t v) { const int a = (short)(v & 0xFFFFu), b = (short)(v >> 16); return a < b ? a : b; }
 
-//  PIPE: software-pipelined chunk loop.  The boundary entries of chunk c+1 are loaded when chunk c starts and are
-//  validated, translated and put into the shared-memory inbox HALF WAY THROUGH chunk c (together with the
-//  substitution tables of chunk c+1), so that the load -> vote -> store -> sync -> load latency chain of the chunk
-//  prologue overlaps the step loop instead of standing between two chunks.
-template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, bool PIPE = false>
+constexpr int kBlock = kRebaseBlock;   // steps per block; nsteps of the 16-bit engine is a multiple of it (host: run_once)
+
+//  HS (round 2): the same slack for the hand-off INSIDE a thread.  The hi sub-lane's top neighbour is the lo
+//  sub-lane's bottom row, so with HS 0 a step cannot start before the previous step's whole row chain has finished:
+//  PRMT -> R dependent max ops -> VIADD -> PRMT, a loop-carried recurrence of 4R+10 cycles that one warp per scheduler
+//  cannot hide (measured: the step time did not move when every memory instruction and the shuffle were taken out).
+//  With HS 1 the hi sub-lane runs two T positions behind the lo sub-lane and consumes the lo bottom row of the step
+//  BEFORE the previous one: the recurrence spans two steps.  Costs one register and 31 more positions of lane skew.
+template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, int HS = 0>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
-  static_assert(SLACK >= 0 && SLACK <= 2, "a shuffled boundary value is consumed 0, 1 or 2 steps after it was sent");
-  constexpr int SK = 2 + SLACK;        // T positions between neighbouring lanes
-  constexpr int SKEW = 31 * SK + 1;    // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
+  static_assert(SLACK == 0 || SLACK == 1, "a shuffled boundary value is consumed in the same step or one step later");
+  static_assert(HS == 0 || HS == 1, "the hi sub-lane trails the lo sub-lane by one or two positions");
+  constexpr int SK = 2 + SLACK + HS;   // T positions between neighbouring lanes
+  constexpr int SKEW = 31 * SK + 1 + HS;   // lane 31's hi sub-lane trails lane 0's lo sub-lane by this
   constexpr int kU = step_unroll(MODE == 0 ? (RB ? 8.5 : 7.5) : (RB ? 5.5 : 4.5), R, kStepUnroll);
   const int lane = w.lane;
   const bool last_lane = lane == 31;
@@ -198,22 +237,19 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
   const int LT = (int)P.LT;            // step arithmetic is 32-bit (the host refuses LT >= 2^30); only ring indices,
                                        // which count steps over all rounds, are 64-bit
-  constexpr int STEP_ALIGN = RB ? kRebaseBlock : kChunk;   // RB: base blocks of consecutive bands must not share a slot
-  const int nsteps = ((LT + SKEW + STEP_ALIGN - 1) / STEP_ALIGN) * STEP_ALIGN;
+  const int nsteps = ((LT + SKEW + kBlock - 1) / kBlock) * kBlock;
   uint32_t best0 = 0, best1 = 0;
   int base = 0, best_abs = 0;          // RB only
   uint32_t floorw = 0;                 // RB only: packed max(-base, -30000)
   Waiter wt{P.spin_limit, false};
   // P is picked at run time between the two halves of a launch, so every P.field inside a loop is a constant load
-  // through a register index; the two that the chunk loop needs are kept in registers.
+  // through a register index; the one the chunk loop needs is kept in a register.
   // (measured: +4.8 % on cfg2 with one warp per scheduler, -2.5 % with two warps per scheduler: only the former do it)
   const uint64_t* t_packed_reg = P.t_packed;
-  long long* const prof_reg = P.prof;
 #if SWB_DEVICE_CODE
   if (SHORT) asm volatile("" : "+l"(t_packed_reg));
 #endif
 #define SWB_T_PACKED (SHORT ? t_packed_reg : P.t_packed)
-#define SWB_PROF (SHORT ? prof_reg : P.prof)
 
   for (long long band = P.ring_offset + lw; band < P.NB; band += P.ring_total) {
     const bool zero_src = band == 0 || (P.dbg & 2);
@@ -236,6 +272,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     // stream restarts at 0 every band (safe: see DESIGN.md, hand-off protocol).
     const long long sbase = (band / P.ring_total) * (long long)nsteps;
     const long long in_base = first_local ? 0 : sbase, out_base = last_local ? 0 : sbase;
+    const bool check_sink = has_sink && !last_local;                     // ring back-pressure applies
 
     // ---- per-band constants: PRMT selectors of this thread's 2*R rows
     uint32_t sel[R];
@@ -253,7 +290,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     uint32_t Ho[R], E[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { Ho[r] = nopen; E[r] = nopen; }
-    uint32_t Fbot = nopen, up_prev = nopen, xsend = nopen, yold = nopen, yold2 = nopen, Thi = padw;
+    uint32_t Fbot = nopen, up_prev = nopen, xsend = nopen, yold = nopen, Thi = padw;
+    uint32_t HoLast_d = nopen, Fbot_d = nopen, Thi_d = padw;   // HS: the lo sub-lane's bottom row / table word, one step older
     if (RB) { base = 0; floorw = 0; best0 = 0; best1 = 0; }   // every band starts at T position 0, where all scores are small
     // base entries live in the second half of a link ring: one {base, tag} per kRebaseBlock producer steps
     // (on the full-length ext stream, which restarts every band, four bands' worth of base entries rotate, so a
@@ -279,71 +317,39 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     //      speculative read of this lane's first boundary entry (and, re-based mode, of its producer's base)
     uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(SWB_T_PACKED + ((kChunk + lane) >> 5)) : 0ull;
     uint2 epref = make_uint2(0u, 0u), bpref = make_uint2(0u, 0u);
-    if (!zero_src && SLACK + lane < LT) {
+    bool live = !zero_src;             // warp-uniform: top boundary entries are expected (false: zero border, or after a timeout)
+    if (live && SLACK + lane < LT) {
       const long long j = in_base + SLACK + lane + SKEW;
       epref = ld_entry(in + (j & in_mask));
       if (RB) bpref = ld_entry(in_bases + ((j >> 8) & inb_mask));
     }
-    if (SLACK && !zero_src) {
-      // With slack steps lane 0 consumes at step i what was shuffled at step i-SLACK; nothing is shuffled before
-      // step 0, so the boundary values of T positions 0 .. SLACK-1 are handed to lane 0 here.  (Every band starts
-      // with base 0, so no translation is needed in re-based mode.)
-#pragma unroll
-      for (int d = 0; d < SLACK; ++d) {
-        if (d < LT) {                                               // warp-uniform
-          const long long j0 = in_base + SKEW + d;
-          const uint32_t v0 = wait_entry(P, w, true, in + (j0 & in_mask), in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu),
-                                         ld_entry(in + (j0 & in_mask)), wt);
-          if (lane == 0) { if (d == SLACK - 1) yold = v0; else yold2 = v0; }
-        }
-      }
+    if (SLACK && live) {
+      // With the slack step lane 0 consumes at step i what was shuffled at step i-1; nothing is shuffled before
+      // step 0, so the boundary value of T position 0 is handed to lane 0 here.  (Every band starts with base 0,
+      // so no translation is needed in re-based mode.)
+      const long long j0 = in_base + SKEW;
+      const uint32_t v0 = wait_entry(P, w, true, in + (j0 & in_mask), in_tag | ((uint32_t)(j0 >> in_shift) & 0xFFu),
+                                     ld_entry(in + (j0 & in_mask)), wt);
+      if (lane == 0) yold = v0;
+      live = !wt.aborted;
     }
-    if (PIPE) {
-      // chunk 0's top boundary is fetched here, before the loop; every later chunk's half way through the chunk before
-      const int q = SLACK + lane;
-      uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
-      if (!zero_src) {
-        const bool need = q < LT;
-        const long long j = in_base + q + SKEW;
-        const uint32_t got = wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
-        if (need) v = got;
-        if (RB) {
-          const long long bj = j >> 8;
-          const uint32_t pb = wait_entry(P, w, need, in_bases + (bj & inb_mask), in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
-          if (need) v = add16x2(v, pack2((int)pb - base));          // base == 0 here
-        }
-      }
-      sm->inbox[q & (kInbox - 1)] = v;
-      sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
-    }
-
+#ifdef SWB_ENABLE_PROF
+    long long prof_pro = 0, prof_steps = 0, prof_polls = 0, prof_chunks = 0;
 #if SWB_DEVICE_CODE
-    if (SWB_PROF && lane == 31 && SWB_PROF[8 * lw + 4] == 0) {
+    if (P.prof && lane == 31 && P.prof[8 * lw + 4] == 0) {
       unsigned long long gt; unsigned smid;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      SWB_PROF[8 * lw + 4] = (long long)gt; SWB_PROF[8 * lw + 6] = (long long)smid;
+      P.prof[8 * lw + 4] = (long long)gt; P.prof[8 * lw + 6] = (long long)smid;
     }
 #endif
-    for (int i0 = 0; i0 < nsteps; i0 += kChunk) {
-#if SWB_DEVICE_CODE
-      const long long tp0 = SWB_PROF ? clock64() : 0;
-      const long long bud0 = wt.budget;
 #endif
-      // (a) substitution tables for T positions [i0+32, i0+64); fetch the word after that
-      auto fill_tables = [&]() {
-        const int q = i0 + kChunk + lane;
-        uint32_t c = 4;
-        if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
-        const uint32_t tw = table_word(c, padw, flip);
-        sm->tab[q & (kTabRing - 1)] = tw;
-        sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
-        twpref = (q + kChunk < LT) ? ld_early_u64(SWB_T_PACKED + ((q + kChunk) >> 5)) : 0ull;
-      };
-      if (!PIPE && !(SWB_KNOCK & 32)) fill_tables();
-      // (a') re-based mode: every kRebaseBlock steps re-centre the registers around the live score level
-      if (RB && (i0 & (kRebaseBlock - 1)) == 0) {
-        if (i0 > 0) {
+
+    for (int i8 = 0; i8 < nsteps; i8 += kBlock) {
+      // ================= once per block of 256 steps =================
+      // (a') re-based mode: re-centre the registers around the live score level
+      if (RB) {
+        if (i8 > 0) {
           uint32_t mxw = Ho[0], mnw = Ho[0];
 #pragma unroll
           for (int r = 1; r < R; ++r) { mxw = max16x2(mxw, Ho[r]); mnw = min16x2(mnw, Ho[r]); }
@@ -360,214 +366,188 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 #pragma unroll
             for (int r = 0; r < R; ++r) { Ho[r] = add16x2(Ho[r], dw); E[r] = add16x2(E[r], dw); }
             Fbot = add16x2(Fbot, dw); up_prev = add16x2(up_prev, dw); xsend = add16x2(xsend, dw); yold = add16x2(yold, dw);
-            yold2 = add16x2(yold2, dw);
+            if (HS) { HoLast_d = add16x2(HoLast_d, dw); Fbot_d = add16x2(Fbot_d, dw); }
             base += delta;
             floorw = pack2(-base > -30000 ? -base : -30000);
-            if (PIPE) {
-              // this chunk's inbox entries were translated to the old base half a chunk ago (by this same lane)
-              const int q = i0 + SLACK + lane;
-              uint32_t v = add16x2(nopen, floorw);
-              if (!zero_src && q < LT) v = add16x2(sm->inbox[q & (kInbox - 1)], dw);
-              sm->inbox[q & (kInbox - 1)] = v;
-              sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
-            }
           }
         }
         // tell the band below which base the entries of this block are relative to
-        if (emit) st_entry(out_bases + (((out_base + i0) >> 8) & outb_mask), (uint32_t)base,
-                           out_tag | ((uint32_t)(((out_base + i0) >> 8) >> out_shift) & 0xFFu));
+        if (emit) st_entry(out_bases + (((out_base + i8) >> 8) & outb_mask), (uint32_t)base,
+                           out_tag | ((uint32_t)(((out_base + i8) >> 8) >> out_shift) & 0xFFu));
       }
-      // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): wait for the producer
-      bool spec = false;
-      const uint2* spec_e = in;
-      const uint2* spec_b = in;
-      // PIPE: the same for the NEXT chunk, called half way through this one; its entries were requested at (b0)
-      long long pj = 0;
-      bool pneed = false;
-      auto fill_inbox_next = [&]() {
-        const int q = i0 + kChunk + SLACK + lane;
-        uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
-        if (!zero_src) {                                                  // warp-uniform branch
-          const uint32_t got = wait_entry(P, w, pneed, in + (pj & in_mask), in_tag | ((uint32_t)(pj >> in_shift) & 0xFFu), epref, wt);
-          if (pneed) v = got;
-          if (RB) {
-            const long long bj = pj >> 8;
-            const uint32_t pb = wait_entry(P, w, pneed, in_bases + (bj & inb_mask), in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
-            if (pneed) {
-              const int diff = (int)pb - base;
-              if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
-              v = add16x2(v, pack2(diff));
-            }
-          }
-        }
-        sm->inbox[q & (kInbox - 1)] = v;
-        sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
-      };
-      if (PIPE) {
-        // (b0) request the next chunk's entries now; they are looked at 16 steps from here
-        const int q = i0 + kChunk + SLACK + lane;
-        pneed = q < LT;
-        pj = in_base + q + SKEW;
-        if (!zero_src && pneed) {
-          epref = ld_entry(in + (pj & in_mask));
-          if (RB) bpref = ld_entry(in_bases + ((pj >> 8) & inb_mask));
-        }
-        if (lane == 0 && (i0 & 255) == 0)
-          st_progress(my_progress, (unsigned long long)(sbase + i0 + SLACK + kChunk));
-      } else {
-        const int q = i0 + SLACK + lane;
-        uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
-        if (!zero_src) {                                                  // warp-uniform branch
-          const bool need = q < LT;
-          const long long j = in_base + q + SKEW;                         // producer step that emitted q
-          const uint32_t got =
-              wait_entry(P, w, need, in + (j & in_mask), in_tag | ((uint32_t)(j >> in_shift) & 0xFFu), epref, wt);
-          if (need) v = got;
-          spec = q + kChunk < LT;                                   // next chunk's entry: loaded speculatively,
-          spec_e = in + ((j + kChunk) & in_mask);                   // half a chunk from now (between the two step loops)
-          if (RB) {
-            // translate from the producer's base (published once per block) into ours
-            const long long bj = j >> 8;
-            const uint32_t pb = wait_entry(P, w, need, in_bases + (bj & inb_mask),
-                                           in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu), bpref, wt);
-            if (need) {
-              const int diff = (int)pb - base;
-              if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
-              v = add16x2(v, pack2(diff));
-            }
-            spec_b = in_bases + (((j + kChunk) >> 8) & inb_mask);
-          }
-        }
-        sm->inbox[q & (kInbox - 1)] = v;
-        sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
-        if (lane == 0 && (i0 & 255) == 0)
-          st_progress(my_progress, (unsigned long long)(sbase + i0 + SLACK + kChunk));
-      }
+      // every boundary entry of the steps before this block has been read: tell the producer (ring back-pressure)
+      if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + i8 + SLACK));
       // (c) ring back-pressure: never overwrite an entry the consumer has not read yet
-      if (has_sink && !last_local && ((sbase + i0) & 1023) == 0 && sbase + i0 + 1024 > (long long)out_mask + 1) {
-        const unsigned long long need = (unsigned long long)(sbase + i0 + 1024 - ((long long)out_mask + 1));
-        wait_progress(P, w, sink_progress, need, band, i0, wt);
+      if (check_sink && ((sbase + i8) & 1023) == 0 && sbase + i8 + 1024 > (long long)out_mask + 1) {
+        const unsigned long long need = (unsigned long long)(sbase + i8 + 1024 - ((long long)out_mask + 1));
+        wait_progress(P, w, sink_progress, need, band, i8, wt);
       }
-      w.sync();
-#if SWB_DEVICE_CODE
-      const long long tp1 = SWB_PROF ? clock64() : 0;
+
+      for (int i0 = i8; i0 < i8 + kBlock; i0 += kChunk) {
+        // ================= once per chunk of 32 steps: straight-line code =================
+#if defined(SWB_ENABLE_PROF) && SWB_DEVICE_CODE
+        const long long tp0 = clock64();
+        const long long bud0 = wt.budget;
+#endif
+        // this chunk's tables were stored a chunk ago: start the first table load now, its latency hides behind the
+        // prologue instead of standing in front of the first step
+        const uint32_t* tabp = sm->tab + ((i0 - SK * lane) & (kTabRing - 1));
+        uint32_t Tnext = tabp[0];
+        // (a) substitution tables for T positions [i0+32, i0+64); fetch the word after that
+        {
+          const int q = i0 + kChunk + lane;
+          uint32_t c = 4;
+          if (q < LT) c = (uint32_t)(twpref >> (2 * (q & 31))) & 3u;
+          const uint32_t tw = table_word(c, padw, flip);
+          sm->tab[q & (kTabRing - 1)] = tw;
+          sm->tab[(q & (kTabRing - 1)) + kTabRing] = tw;
+          twpref = (q + kChunk < LT) ? ld_early_u64(SWB_T_PACKED + ((q + kChunk) >> 5)) : 0ull;
+        }
+        // (b) top boundary for lane 0's positions [i0+SLACK, i0+SLACK+32): normally already here (loaded half a
+        //     chunk ago); one vote decides whether the out-of-line poll loop is needed
+        const int q = i0 + SLACK + lane;
+        const long long j = in_base + q + SKEW;                           // producer step that emitted q
+        const bool need = live && q < LT;
+        {
+          const uint32_t want = in_tag | ((uint32_t)(j >> in_shift) & 0xFFu);
+          const long long bj = j >> 8;
+          const uint32_t bwant = in_tag | ((uint32_t)(bj >> in_shift) & 0xFFu);
+          const bool ok = !need || (epref.y == want && (!RB || bpref.y == bwant));
+          if (!w.all(ok)) {                       // rare: out of line; the entries are re-read here once they are valid
+            wt.budget = poll_boundary(P, w, need, in + (j & in_mask), want, in_bases + (bj & inb_mask), bwant, RB, wt.budget);
+            if (wt.budget < 0) { wt.aborted = true; live = false; }
+            else if (need) { epref = ld_entry(in + (j & in_mask)); if (RB) bpref = ld_entry(in_bases + (bj & inb_mask)); }
+          }
+          uint32_t v = RB ? add16x2(nopen, floorw) : nopen;
+          if (need && live) {
+            v = epref.x;
+            if (RB) {                  // translate from the producer's base (published once per block) into ours
+              const int diff = (int)bpref.x - base;
+              if (diff > 30000 || diff < -30000) atomic_or_i32(P.result + 1, STATUS_REBASE_RANGE);
+              v = add16x2(v, pack2(diff));
+            }
+          }
+          sm->inbox[q & (kInbox - 1)] = v;
+          sm->inbox[(q & (kInbox - 1)) + kInbox] = v;
+        }
+        // next chunk's entry: loaded speculatively half a chunk from now (between the two step loops)
+        const bool spec = live && q + kChunk < LT;
+        const uint2* spec_e = in + ((j + kChunk) & in_mask);
+        const uint2* spec_b = in_bases + (((j + kChunk) >> 8) & inb_mask);
+        w.sync();
+#if defined(SWB_ENABLE_PROF) && SWB_DEVICE_CODE
+        const long long tp1 = clock64();
 #endif
 
-      const uint32_t* tabp = sm->tab + ((i0 - SK * lane) & (kTabRing - 1));
-      const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
-      uint2* outp = out + ((out_base + i0) & out_mask);
-      const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
+        const uint32_t* inbp = sm->inbox + ((i0 + SLACK) & (kInbox - 1));
+        uint2* outp = out + ((out_base + i0) & out_mask);
+        const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
 
-      uint32_t Tnext = tabp[0], xnext = inbp[0];       // loaded one step ahead of use
-      auto step = [&](const int k) {
-        const uint32_t Tlo = Tnext;
-        const uint32_t xin = xnext;
-        if (!(SWB_KNOCK & 4)) Tnext = tabp[k + 1]; else Tnext = Tnext * 5u + 1u;
-        if (!(SWB_KNOCK & 2)) xnext = inbp[k + 1];
-        const uint32_t xs = (SWB_KNOCK & 2) ? xsend : (last_lane ? xin : xsend);
-        const uint32_t ynew = (SWB_KNOCK & 8) ? (xs ^ (uint32_t)k) : w.shfl(xs, src_lane);
-        const uint32_t yuse = SLACK == 0 ? ynew : (SLACK == 1 ? yold : yold2);
-        yold2 = yold;
-        yold = ynew;
-        uint32_t upHo, F;
-        if (MODE == 0) {
-          upHo = prmt(yuse, Ho[R - 1], 0x5410u);   // lo <- neighbour's bottom (H-open), hi <- own lo bottom
-          F = prmt(yuse, Fbot, 0x5432u);           // lo <- neighbour's bottom F,      hi <- own lo bottom F
-        } else {
-          upHo = prmt(yuse, Ho[R - 1], 0x5432u);   // linear mode ships the whole H-open word
-          F = 0;
-        }
-        uint32_t diag = up_prev;
-        up_prev = upHo;
-        if (SHORT) {
-          // Row loop with ONE dependent instruction per row (used with one warp per scheduler, where the
-          // dependency chain and not the issue rate limits a step).  With m = max(diag + s, E, 0):
-          //   F[r]  = max(F[r-1] - min(ext, open), m[r-1] - open)   because H[r-1] = max(m[r-1], F[r-1]);
-          //   Ho[r] = H[r] - open = max(m[r], F[r]) - open.
-          // Only F (affine) or H (linear) is carried from row to row; everything else depends on the previous
-          // column alone.  Row 0 takes the true neighbour values (upHo, F) and the plain recurrence.
-          uint32_t X = upHo, hprev = 0;
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const uint32_t s = prmt(Tlo, Thi, sel[r]);
-            const uint32_t old = Ho[r];
-            uint32_t h;
-            if (MODE == 0) {
-              E[r] = addmax16x2(E[r], next, old);
-              const uint32_t m = RB ? max16x2(addmax16x2(diag, s, E[r]), floorw) : addmaxrelu16x2(diag, s, E[r]);
-              F = addmax16x2(F, r == 0 ? next : fnext, X);
-              X = add16x2(m, nopen);
-              h = max16x2(m, F);
-            } else if (RB) {
-              const uint32_t t = max3_16x2(add16x2(diag, s), old, floorw);
-              h = r == 0 ? max16x2(t, X) : addmax16x2(hprev, nopen, t);
-            } else {
-              const uint32_t t = addmax16x2(diag, s, old);
-              h = r == 0 ? maxrelu16x2(t, X) : addmaxrelu16x2(hprev, nopen, t);
-            }
-            hprev = h;
-            Ho[r] = add16x2(h, nopen);
-            diag = old;
-            if (SWB_KNOCK & 16) { if (r == R - 1) best0 = max16x2(best0, h); }
-            else if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+        uint32_t xnext = inbp[0];                        // loaded one step ahead of use (like Tnext)
+        auto step = [&](const int k) {
+          const uint32_t Tlo = Tnext;
+          const uint32_t xin = xnext;
+          Tnext = tabp[k + 1];
+          xnext = inbp[k + 1];
+          const uint32_t xs = last_lane ? xin : xsend;
+          const uint32_t ynew = w.shfl(xs, src_lane);
+          const uint32_t yuse = SLACK ? yold : ynew;
+          yold = ynew;
+          // what the hi sub-lane sees above it: the lo sub-lane's bottom row after the previous step (HS 0) or after
+          // the step before that (HS 1); likewise its table word
+          const uint32_t lo_bottom = HS ? HoLast_d : Ho[R - 1];
+          const uint32_t lo_bottom_f = HS ? Fbot_d : Fbot;
+          const uint32_t Thi_use = HS ? Thi_d : Thi;
+          if (HS) { HoLast_d = Ho[R - 1]; Fbot_d = Fbot; Thi_d = Thi; }
+          uint32_t upHo, F;
+          if (MODE == 0) {
+            upHo = prmt(yuse, lo_bottom, 0x5410u);   // lo <- neighbour's bottom (H-open), hi <- own lo bottom
+            F = prmt(yuse, lo_bottom_f, 0x5432u);    // lo <- neighbour's bottom F,      hi <- own lo bottom F
+          } else {
+            upHo = prmt(yuse, lo_bottom, 0x5432u);   // linear mode ships the whole H-open word
+            F = 0;
           }
-        } else {
-          // Fewest instructions per row (used with two warps per scheduler, where the issue rate is the limit).
-          uint32_t Hup = upHo;
+          uint32_t diag = up_prev;
+          up_prev = upHo;
+          if (SHORT) {
+            // Row loop with ONE dependent instruction per row (used with one warp per scheduler, where the
+            // dependency chain and not the issue rate limits a step).  With m = max(diag + s, E, 0):
+            //   F[r]  = max(F[r-1] - min(ext, open), m[r-1] - open)   because H[r-1] = max(m[r-1], F[r-1]);
+            //   Ho[r] = H[r] - open = max(m[r], F[r]) - open.
+            // Only F (affine) or H (linear) is carried from row to row; everything else depends on the previous
+            // column alone.  Row 0 takes the true neighbour values (upHo, F) and the plain recurrence.
+            uint32_t X = upHo, hprev = 0;
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const uint32_t s = prmt(Tlo, Thi, sel[r]);
-            const uint32_t d = add16x2(diag, s);
-            const uint32_t old = Ho[r];
-            uint32_t h;
-            if (MODE == 0) {
-              E[r] = addmax16x2(E[r], next, old);
-              F = addmax16x2(F, next, Hup);
-              h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
-            } else {
-              // non-RB: the clamp at 0 rides on the fused add-max, the second max is the plain full-rate VIMNMX
-              h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max16x2(addmaxrelu16x2(diag, s, old), Hup);
+            for (int r = 0; r < R; ++r) {
+              const uint32_t s = prmt(Tlo, Thi_use, sel[r]);
+              const uint32_t old = Ho[r];
+              uint32_t h;
+              if (MODE == 0) {
+                E[r] = addmax16x2(E[r], next, old);
+                const uint32_t m = RB ? max16x2(addmax16x2(diag, s, E[r]), floorw) : addmaxrelu16x2(diag, s, E[r]);
+                F = addmax16x2(F, r == 0 ? next : fnext, X);
+                X = add16x2(m, nopen);
+                h = max16x2(m, F);
+              } else if (RB) {
+                const uint32_t t = max3_16x2(add16x2(diag, s), old, floorw);
+                h = r == 0 ? max16x2(t, X) : addmax16x2(hprev, nopen, t);
+              } else {
+                const uint32_t t = addmax16x2(diag, s, old);
+                h = r == 0 ? maxrelu16x2(t, X) : addmaxrelu16x2(hprev, nopen, t);
+              }
+              hprev = h;
+              Ho[r] = add16x2(h, nopen);
+              diag = old;
+              if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
             }
-            Ho[r] = add16x2(h, nopen);
-            Hup = Ho[r];
-            diag = old;
-            if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+          } else {
+            // Fewest instructions per row (used with two warps per scheduler, where the issue rate is the limit).
+            uint32_t Hup = upHo;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const uint32_t s = prmt(Tlo, Thi_use, sel[r]);
+              const uint32_t d = add16x2(diag, s);
+              const uint32_t old = Ho[r];
+              uint32_t h;
+              if (MODE == 0) {
+                E[r] = addmax16x2(E[r], next, old);
+                F = addmax16x2(F, next, Hup);
+                h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
+              } else {
+                // non-RB: the clamp at 0 rides on the fused add-max, the second max is the plain full-rate VIMNMX
+                h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max16x2(addmaxrelu16x2(diag, s, old), Hup);
+              }
+              Ho[r] = add16x2(h, nopen);
+              Hup = Ho[r];
+              diag = old;
+              if (r & 1) best1 = max16x2(best1, h); else best0 = max16x2(best0, h);
+            }
           }
-        }
-        Fbot = F;
-        xsend = (MODE == 0) ? prmt(Ho[R - 1], Fbot, 0x7632u) : Ho[R - 1];
-        Thi = Tlo;
-        // slot = producer step (always in range); steps whose T position is outside [0,LT) are never read
-        if (!(SWB_KNOCK & 1)) { if (emit) st_entry(outp + k, xsend, otag); }
-      };
-      // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
-      // the speculative boundary loads of the next chunk in between: the band above only has to be
-      // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
+          Fbot = F;
+          xsend = (MODE == 0) ? prmt(Ho[R - 1], Fbot, 0x7632u) : Ho[R - 1];
+          Thi = Tlo;
+          // slot = producer step (always in range); steps whose T position is outside [0,LT) are never read
+          if (emit) st_entry(outp + k, xsend, otag);
+        };
+        // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
+        // the speculative boundary loads of the next chunk in between: the band above only has to be
+        // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
 #pragma unroll (kU)
-      for (int k = 0; k < kChunk / 2; ++k) step(k);
-      if (PIPE) {
-        fill_tables();
-        fill_inbox_next();
-      } else {
+        for (int k = 0; k < kChunk / 2; ++k) step(k);
         if (spec) epref = ld_entry(spec_e);
         if (RB && spec) bpref = ld_entry(spec_b);
-      }
 #pragma unroll (kU)
-      for (int k = kChunk / 2; k < kChunk; ++k) step(k);
-#if SWB_DEVICE_CODE
-      if (SWB_PROF) {
-        const long long tp2 = clock64();
-        long long* pr = SWB_PROF + 8 * lw;
-        if (lane == 31) { pr[0] += tp1 - tp0; pr[1] += tp2 - tp1; pr[3] += 1; }
-        if (lane == 31) pr[2] += bud0 - wt.budget;
-      }
+        for (int k = kChunk / 2; k < kChunk; ++k) step(k);
+#if defined(SWB_ENABLE_PROF) && SWB_DEVICE_CODE
+        { const long long tp2 = clock64(); prof_pro += tp1 - tp0; prof_steps += tp2 - tp1; prof_polls += bud0 - wt.budget; prof_chunks += 1; }
 #endif
+      }
     }
-#if SWB_DEVICE_CODE
-    if (SWB_PROF && lane == 31 && SWB_PROF[8 * lw + 5] == 0) {
-      unsigned long long gt;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      SWB_PROF[8 * lw + 5] = (long long)gt;
+#if defined(SWB_ENABLE_PROF) && SWB_DEVICE_CODE
+    if (P.prof && lane == 31) {
+      long long* pr = P.prof + 8 * lw;
+      pr[0] += prof_pro; pr[1] += prof_steps; pr[2] += prof_polls; pr[3] += prof_chunks;
+      if (pr[5] == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); pr[5] = (long long)gt; }
     }
 #endif
     if (RB) {
@@ -586,7 +566,6 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 }
 
 #undef SWB_T_PACKED
-#undef SWB_PROF
 
 // =================================================================================================
 //  32-bit engine (scores beyond the s16 range): one sub-lane per thread, band = 32*R rows.

@@ -8,13 +8,17 @@ namespace swb {
 // config 2: 8 warps per CTA (two per scheduler), consumed in the same step (SLACK 0)
 // config 3: 4 warps per CTA, consumed in the same step (shortest pipeline; the SHFL latency is covered by
 //           the independent E / substitution work once R is large enough)
-// config 4: 4 warps per CTA, value consumed TWO steps late (SLACK 2: the ~50-cycle SHFL latency leaves the per-step
-//           recurrence) and the pipelined chunk loop (PIPE); packed 16-bit modes only
-// config 5 / 6: measurement variants of 4 (SLACK 1 + PIPE / SLACK 2 without PIPE); packed 16-bit modes only
-constexpr int kNumConfigs = 6;
+// config 4: config 1 plus the same slack for the hand-off inside a thread (HS 1: the hi sub-lane runs two positions
+//           behind the lo sub-lane, which takes the row chain out of the per-step recurrence); packed 16-bit modes only
+constexpr int kNumConfigs = 4;
 SWB_HD int config_wpc(int config) { return config == 2 ? 8 : 4; }
-SWB_HD int config_slack(int config) { return (config == 1 || config == 5) ? 1 : ((config == 4 || config == 6) ? 2 : 0); }
-SWB_HD bool config_pipe(int config) { return config == 4 || config == 5; }
+SWB_HD int config_slack(int config) { return (config == 1 || config == 4) ? 1 : 0; }
+SWB_HD int config_hs(int config) { return config == 4 ? 1 : 0; }
+// steps by which the last sub-lane of a band trails the first (what a band adds to the sweep; entry slot - T position)
+SWB_HD int config_skew(int config, int mode) {
+  const int slack = config_slack(config), hs = config_hs(config);
+  return mode_is_s32(mode) ? 31 * (1 + slack) : 31 * (2 + slack + hs) + 1 + hs;
+}
 
 constexpr int kRowChoices[] = {1, 2, 3, 4, 6, 8, 10, 12, 14, 16};
 constexpr int kNumRowChoices = 10;
@@ -40,7 +44,7 @@ struct EngineLaunch {
 };
 
 #ifdef __CUDACC__
-template <int R, int MODE, int SLACK, int WPC, bool PIPE = false>
+template <int R, int MODE, int SLACK, int WPC, int HS = 0>
 __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineLaunch L) {
   __shared__ WarpSmem sm[WPC];
   WarpCtx w{(int)(threadIdx.x & 31)};
@@ -60,8 +64,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   else if constexpr (MODE == 7) engine_warp_s32<R, SLACK, true, SHORT, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 8) engine_warp_s32<R, SLACK, false, SHORT, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 9) engine_warp_s32<R, SLACK, true, SHORT, true, true>(P, w, lw, &sm[wi]);
-  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT, PIPE>(P, w, lw, &sm[wi]);
-  else engine_warp_s16<R, MODE, SLACK, false, SHORT, PIPE>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT, HS>(P, w, lw, &sm[wi]);
+  else engine_warp_s16<R, MODE, SLACK, false, SHORT, HS>(P, w, lw, &sm[wi]);
 }
 
 template <int MODE>
@@ -70,11 +74,7 @@ static const void* engine_kernel_lookup(int R, int config) {
   if (config < 1 || config > kNumConfigs || (config > 3 && !S16)) return nullptr;
 #define SWB_CASE(RR)                                                             \
   case RR:                                                                       \
-    if constexpr (S16) {                                                         \
-      if (config == 4) return (const void*)sw_engine_kernel<RR, MODE, 2, 4, true>;   \
-      if (config == 5) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, true>;   \
-      if (config == 6) return (const void*)sw_engine_kernel<RR, MODE, 2, 4, false>;  \
-    }                                                                            \
+    if constexpr (S16) { if (config == 4) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 1>; }   \
     return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
          : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \
                        : (const void*)sw_engine_kernel<RR, MODE, 0, 4>;

@@ -38,11 +38,35 @@ class Ring:
         if rc != 0:
             raise SwbError(rc, "swb200_ring_connect_local")
 
+    def connect_root_ipc(self, root_handle: bytes):
+        """Maps rank 0's region too: enables the two-sided sweep over the ring (swb200_ring_connect_root)."""
+        buf = (C.c_char * 64).from_buffer_copy(root_handle)
+        rc = _lib.load().swb200_ring_connect_root(self.handle, buf)
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_connect_root")
+
+    def connect_root_local(self, root: "Ring"):
+        rc = _lib.load().swb200_ring_connect_root_local(self.handle, root.handle)
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_connect_root_local")
+
+    def combine_pending(self) -> bool:
+        return bool(_lib.load().swb200_ring_combine_pending(self.handle))
+
+    def combine(self, stream: int = 0) -> int:
+        """After EVERY rank's partial() has returned: the best alignment crossing the middle row (rank 0; 0 elsewhere)."""
+        out = C.c_int(0)
+        rc = _lib.load().swb200_ring_combine(self.handle, C.c_void_p(stream), C.byref(out))
+        if rc != 0:
+            raise SwbError(rc, "swb200_ring_combine")
+        return out.value
+
     def partial(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int,
-                stream: int = 0, rows: int = 0, config: int = 0, ctas: int = 0, no_linear: bool = False, rebase: int = 0):
+                stream: int = 0, rows: int = 0, config: int = 0, ctas: int = 0, no_linear: bool = False, rebase: int = 0,
+                two_sided: int = 0):
         """This rank's share of one collective call: (partial best score, status bits)."""
         score, status = C.c_int(0), C.c_int(0)
-        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, 0, rebase)
+        p, o = _params(params), _options(lanes, rows, config, ctas, no_linear, 0, rebase, two_sided)
         rc = _lib.load().swb200_ring_score_device(self.handle, C.c_void_p(d_seq1), n, C.c_void_p(d_seq2), m, C.byref(p),
                                                   C.byref(o), C.c_void_p(stream), C.byref(score), C.byref(status))
         if rc != 0:
@@ -70,7 +94,9 @@ class DistributedRingAligner:
         self.ring = _ring_factory(self.ctx, self.rank, self.world, max_stream_len)
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(self.ring.ipc.raw), group=group)
-        self.ring.connect_ipc(handles[(self.rank + 1) % self.world]) if self.world > 1 else self.ring.connect_local(self.ring)
+        if self.world > 1:
+            self.ring.connect_ipc(handles[(self.rank + 1) % self.world])
+            self.ring.connect_root_ipc(handles[0])           # two-sided sweeps: the two middle rows meet on rank 0
         dist.barrier(group=group)
 
     def score(self, d_seq1: int, n: int, d_seq2: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, *, lanes: int = 0,
@@ -93,6 +119,9 @@ class DistributedRingAligner:
                 if rebase == 1 and e.code == -2:      # re-based lanes not safe for these parameters: same on every rank
                     continue
                 raise
+            if self.ring.combine_pending():      # same answer on every rank: the plan depends only on the arguments
+                dist.barrier(group=self.group)   # every rank's kernel has finished: the middle rows are complete on rank 0
+                part = max(part, self.ring.combine(stream))
             t = torch.tensor([part, status & STATUS_S16_OVERFLOW, status & STATUS_TIMEOUT, status & STATUS_REBASE_RANGE],
                              dtype=torch.int32, device=self.reduce_device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)

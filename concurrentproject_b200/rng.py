@@ -1,8 +1,8 @@
 """Portable counter-based sequence generator.
 
 The same function exists in C (oracle/gotoh_oracle.c: oracle_mix64 / oracle_random_acgt) and in
-CUDA (csrc/swb200_gen.cuh); all three are bit-identical, so the GPU path, the oracle and the
-fixtures see the same bytes.  This replaces the reference harness's unseeded
+CUDA (csrc/swb_gen.cu: swb200_gen_*_device); all three are bit-identical, so the GPU path, the oracle
+and the fixtures see the same bytes (tests/test_gpu_gen.py compares them byte for byte).  This replaces the reference harness's unseeded
 ``rand() % 4`` (TestFileWithGPU.cpp:25-36) and its libstdc++-specific
 ``mt19937_64 + uniform_int_distribution`` (cudaSmithM.cu:200-213).
 """
@@ -80,3 +80,33 @@ def mutate(seq: np.ndarray, seed: int, stream: int, sub_rate: float, indel_rate:
     ins = kind == 3
     res[pos[ins] + 1] = _NT[(newc[ins] + 2) & 3]
     return res
+
+
+# ---- the synthetic inputs of BASELINE configs 4 and 5, one pair at a time --------------------
+# csrc/swb_gen.cu generates whole batches of these in HBM; the functions below regenerate any single pair (by its
+# global pair id) on the host, for the oracle sample of bench.py and for tests/test_gpu_gen.py.
+
+def read_pair(seed: int, pair_id: int, read_len: int = 150, window_len: int = 1000):
+    """(read, window) of BASELINE config 4: the window is window_len random bases (stream 2*pair_id); even pairs carry
+    a read cut from the window (offset mix64(seed, 2*pair_id+1, 2**40) % (window_len - read_len - 15)) with 5 %
+    substitutions and 1 % indels, odd pairs a read of read_len unrelated random bases (stream 2*pair_id+1)."""
+    window = random_acgt(seed, 2 * pair_id, window_len)
+    if pair_id % 2 == 0:
+        off = int(mix64(seed, 2 * pair_id + 1, np.uint64(1 << 40))) % (window_len - read_len - 15)
+        read = _first(mutate(window[off:off + read_len + 16], seed, 2 * pair_id + 1, 0.05, 0.01), read_len)
+    else:
+        read = random_acgt(seed, 2 * pair_id + 1, read_len)
+    return read, window
+
+
+def long_pair(seed: int, pair_id: int, length: int = 10000):
+    """(seq1, seq2) of BASELINE config 5: seq1 = length random bases (stream 2*pair_id); seq2 = the same stretch (plus
+    320 spare bases) with 10 % substitutions and 2 % single-base indels, cut to length."""
+    src = random_acgt(seed, 2 * pair_id, length + 320)
+    return src[:length].copy(), _first(mutate(src, seed, 2 * pair_id + 1, 0.10, 0.02), length)
+
+
+def _first(a: np.ndarray, n: int) -> np.ndarray:
+    if len(a) >= n:
+        return a[:n].copy()
+    return np.concatenate([a, np.full(n - len(a), ord("A"), dtype=np.uint8)])

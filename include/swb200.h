@@ -182,6 +182,25 @@ SWB200_API int swb200_score_banded_batch(const unsigned char* seq1_all, const lo
 SWB200_API int swb200_batch_score_banded(swb200_batch* batch, int band_lo, int band_hi, const swb200_params* p,
                                          const swb200_options* opt, void* stream, int* d_scores);
 
+/* ---- seeded synthetic inputs, generated in HBM -----------------------------------------
+ * The portable counter-based generator of concurrentproject_b200/rng.py and oracle/gotoh_oracle.c on the device,
+ * bit-identical to both: symbol k of stream s = 2 bits of mix64(seed, s, k / 32) -> "ACGT".  Replaces the reference
+ * harness's unseeded rand() % 4 (TestFileWithGPU.cpp:25-36).  All pointers are DEVICE pointers on `device`.
+ *   gen_random      length symbols of one stream (rng.random_acgt)
+ *   gen_read_pairs  BASELINE config 4, pairs first_pair .. first_pair+npairs-1 (global ids, so shards of one batch are
+ *                   generated independently): window = window_len random bases; even pairs: the read is a substring
+ *                   of the window with 5 % substitutions and 1 % indels, odd pairs: read_len random bases
+ *                   (rng.read_pair).  d_reads: npairs*read_len bytes, d_windows: npairs*window_len bytes.
+ *   gen_long_pairs  BASELINE config 5: seq1 = len random bases, seq2 = the same stretch with 10 % substitutions and
+ *                   2 % short indels, cut to len (rng.long_pair).  d_seq1, d_seq2: npairs*len bytes each. */
+SWB200_API int swb200_gen_random_device(int device, unsigned long long seed, unsigned long long stream_id, long long length,
+                                        unsigned char* d_out, void* stream);
+SWB200_API int swb200_gen_read_pairs_device(int device, unsigned long long seed, long long first_pair, long long npairs,
+                                            int read_len, int window_len, unsigned char* d_reads, unsigned char* d_windows,
+                                            void* stream);
+SWB200_API int swb200_gen_long_pairs_device(int device, unsigned long long seed, long long first_pair, long long npairs,
+                                            int len, unsigned char* d_seq1, unsigned char* d_seq2, void* stream);
+
 /* ---- one very long pair over a ring of GPUs ------------------------------------------------------
  * All warps of all GPUs form one ring of DP bands: the last warp of GPU g pushes its
  * boundary stream straight into GPU g+1's memory (peer stores over NVLink), so neighbouring GPUs

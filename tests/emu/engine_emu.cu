@@ -32,22 +32,21 @@ static std::vector<uint8_t> read_file(const char* path) {
 
 // SLACK 1 = launch config 1, SLACK 0 = launch config 2 (the product pairs SLACK 0 / 8 warps per CTA with the
 // long-chain row loop); EMU_SHORT=0/1 overrides the row-loop flavour.
-static int g_short = -1, g_pipe = 0;
+static int g_short = -1, g_hs = 0;
 template <int R, int MODE, int SLACK>
 static void run_lane(const EngineParams* P, WarpShared* ws, int lane, int lw, WarpSmem* sm) {
   WarpCtx w{lane, ws};
-  const bool sh = g_short < 0 ? SLACK >= 1 : g_short != 0;
+  const bool sh = g_short < 0 ? SLACK == 1 : g_short != 0;
   if constexpr (MODE != 2 && MODE != 6 && MODE != 8) {
-    if (g_pipe) {          // EMU_PIPE=1: the software-pipelined chunk loop (launch configs 4, 5)
-      if (MODE >= 3) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true, true>(*P, w, lw, sm);
-      else engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK, false, true, true>(*P, w, lw, sm);
+    if (g_hs) {            // EMU_HS=1: slack for the hand-off inside a thread as well (launch config 4)
+      if (MODE >= 3) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true, 1>(*P, w, lw, sm);
+      else engine_warp_s16<R, (MODE < 2 ? MODE : 0), SLACK, false, true, 1>(*P, w, lw, sm);
       return;
     }
   }
-  constexpr int S32 = SLACK > 1 ? 1 : SLACK;      // the 32-bit engine knows slack 0 and 1
-  if (MODE == 2) { if (sh) engine_warp_s32<R, S32, false, true>(*P, w, lw, sm); else engine_warp_s32<R, S32, false, false>(*P, w, lw, sm); }
-  else if (MODE == 6) { if (sh) engine_warp_s32<R, S32, false, true, true>(*P, w, lw, sm); else engine_warp_s32<R, S32, false, false, true>(*P, w, lw, sm); }
-  else if (MODE == 8) { if (sh) engine_warp_s32<R, S32, false, true, true, true>(*P, w, lw, sm); else engine_warp_s32<R, S32, false, false, true, true>(*P, w, lw, sm); }
+  if (MODE == 2) { if (sh) engine_warp_s32<R, SLACK, false, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false>(*P, w, lw, sm); }
+  else if (MODE == 6) { if (sh) engine_warp_s32<R, SLACK, false, true, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false, true>(*P, w, lw, sm); }
+  else if (MODE == 8) { if (sh) engine_warp_s32<R, SLACK, false, true, true, true>(*P, w, lw, sm); else engine_warp_s32<R, SLACK, false, false, true, true>(*P, w, lw, sm); }
   else if (MODE >= 3) {
     if (sh) engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, true>(*P, w, lw, sm);
     else engine_warp_s16<R, (MODE >= 3 ? MODE - 3 : 0), SLACK, true, false>(*P, w, lw, sm);
@@ -61,10 +60,10 @@ typedef void (*lane_fn)(const EngineParams*, WarpShared*, int, int, WarpSmem*);
 
 template <int R>
 static lane_fn pick2(int mode, int slack) {
-  if (mode == 0) return slack == 2 ? run_lane<R, 0, 2> : slack ? run_lane<R, 0, 1> : run_lane<R, 0, 0>;
-  if (mode == 1) return slack == 2 ? run_lane<R, 1, 2> : slack ? run_lane<R, 1, 1> : run_lane<R, 1, 0>;
-  if (mode == 3) return slack == 2 ? run_lane<R, 3, 2> : slack ? run_lane<R, 3, 1> : run_lane<R, 3, 0>;
-  if (mode == 4) return slack == 2 ? run_lane<R, 4, 2> : slack ? run_lane<R, 4, 1> : run_lane<R, 4, 0>;
+  if (mode == 0) return slack ? run_lane<R, 0, 1> : run_lane<R, 0, 0>;
+  if (mode == 1) return slack ? run_lane<R, 1, 1> : run_lane<R, 1, 0>;
+  if (mode == 3) return slack ? run_lane<R, 3, 1> : run_lane<R, 3, 0>;
+  if (mode == 4) return slack ? run_lane<R, 4, 1> : run_lane<R, 4, 0>;
   if (mode == 6) return slack ? run_lane<R, 6, 1> : run_lane<R, 6, 0>;      // 32-bit lanes + end cell
   if (mode == 8) return slack ? run_lane<R, 8, 1> : run_lane<R, 8, 0>;      // anchored recurrence + position of the maximum
   return slack ? run_lane<R, 2, 1> : run_lane<R, 2, 0>;
@@ -90,7 +89,7 @@ int main(int argc, char** argv) {
       ge = argc > 12 ? atoi(argv[12]) : 1;
   long long link_len = argc > 13 ? atoll(argv[13]) : 4096;
   if (getenv("EMU_SHORT")) g_short = atoi(getenv("EMU_SHORT"));
-  if (getenv("EMU_PIPE")) g_pipe = atoi(getenv("EMU_PIPE"));
+  if (getenv("EMU_HS")) g_hs = atoi(getenv("EMU_HS"));
   lane_fn fn = pick(R, mode, slack);
   if (!fn) { fprintf(stderr, "unsupported R\n"); return 2; }
 
@@ -102,8 +101,8 @@ int main(int argc, char** argv) {
 
   const int rpb = rows_per_band(R, mode);
   const int NB = (int)((LQ + rpb - 1) / rpb);
-  const long long skew = (mode == 2 || mode == 6 || mode == 8) ? 31 * (1 + slack) : 31 * (2 + slack) + 1;
-  const int align = mode >= 3 ? kRebaseBlock : kChunk;
+  const long long skew = (mode == 2 || mode == 6 || mode == 8) ? 31 * (1 + slack) : 31 * (2 + slack + g_hs) + 1 + g_hs;
+  const int align = (mode == 2 || mode == 6 || mode == 8) ? kChunk : kBlock;
   long long nsteps = ((LT + skew + align - 1) / align) * align;
   long long ext_len = 1; int ext_shift = 0;
   while (ext_len < nsteps + kChunk) { ext_len <<= 1; ++ext_shift; }

@@ -27,16 +27,16 @@ def emu():
         subprocess.run(["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(EMU),
                         str(src), "-lpthread"], check=True, cwd=EMU_DIR)
 
-    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp"), final_row=False, short=None, pipe=False):
+    def run(q, t, R, mode, slack, W, G, p=O.DEFAULT, link_len=4096, epoch=5, tmp=Path("/tmp"), final_row=False, short=None, hs=False):
         qf, tf, ff = tmp / "swb_emu_q.bin", tmp / "swb_emu_t.bin", tmp / "swb_emu_final.bin"
         qf.write_bytes(bytes(q)); tf.write_bytes(bytes(t))
         ma, mi, gi, ge = p
         env = dict(os.environ, EMU_FINAL=str(ff)) if final_row else dict(os.environ)
         env.pop("EMU_FINAL", None) if not final_row else None
         env.pop("EMU_SHORT", None)
-        env.pop("EMU_PIPE", None)
-        if pipe:                                    # the software-pipelined chunk loop (launch configs 4, 5)
-            env["EMU_PIPE"] = "1"
+        env.pop("EMU_HS", None)
+        if hs:                                      # launch config 4: slack inside a thread as well
+            env["EMU_HS"] = "1"
         if short is not None:                       # row-loop flavour; default: short chain iff slack == 1
             env["EMU_SHORT"] = str(int(short))
         out = subprocess.run([str(EMU), str(qf), str(tf), *map(str, [R, mode, slack, W, G, epoch, ma, mi, gi, ge, link_len])],

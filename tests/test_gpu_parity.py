@@ -181,8 +181,61 @@ def test_ring_of_virtual_ranks_on_one_gpu(api):
         assert all(st == 0 for _, st in parts), parts
         assert max(s for s, _ in parts) == want, (parts, want)
         assert sum(1 for s, _ in parts if s > 0) >= 2           # the work really was spread over the ranks
+    # the same ring swept from BOTH ends: two half problems, each a ring over all ranks; the ranks owning the two last
+    # bands store the middle rows into rank 0's region, rank 0 combines once every rank is done
+    for r in range(world):
+        rings[r].connect_root_local(rings[0])
+    for lanes_kw in (dict(no_linear=True), dict(no_linear=False), dict(no_linear=True, rebase=1)):
+        parts = [rings[r].partial(ta.data_ptr(), len(a), tb.data_ptr(), len(b), lanes=16, rows=4, ctas=6, config=1, two_sided=1,
+                                  **lanes_kw) for r in range(world)]
+        assert all(st == 0 for _, st in parts), parts
+        assert all(rings[r].combine_pending() for r in range(world))
+        crossing = [rings[r].combine() for r in range(world)]
+        assert crossing[1:] == [0] * (world - 1)                # only the root holds the middle rows
+        assert max([s for s, _ in parts] + crossing) == want, (parts, crossing, want)
+    # an alignment that crosses the middle row is only found by the combination step
+    q = rng.random_acgt(601, 0, 16000)
+    t = np.concatenate([rng.random_acgt(601, 1, 5000), q[7000:9000], rng.random_acgt(601, 2, 5000)])
+    tq = torch.from_numpy(q.copy()).cuda(); tt = torch.from_numpy(t.copy()).cuda()
+    parts = [rings[r].partial(tq.data_ptr(), len(q), tt.data_ptr(), len(t), lanes=16, rows=4, ctas=6, config=1, two_sided=1)
+             for r in range(world)]
+    crossing = [rings[r].combine() for r in range(world)]
+    assert max(s for s, _ in parts) < 2000 <= crossing[0] == O.gotoh_mt(q, t)
     for x in rings:
         x.close()
+
+
+def test_pinned_scores_of_the_long_pairs(api):
+    """BASELINE config 3 (4 000 000 x 4 000 000, seed 3) and the 1 M pair, against scores pinned on the CPU by
+    oracle/gotoh_fast.c (tests/golden/large_scores.json; cfg3 took 24 minutes on 8 cores) -- in re-based 16-bit lanes
+    (the default for these sizes) and, for the 1 M pair, in 32-bit lanes and through the general affine kernel too."""
+    import torch
+    big = load_json("large_scores.json")
+    ctx = api.Context(0)
+    for name, variants in (("ring400k", [{}, {"lanes": 32}, {"no_linear": True}, {"two_sided": -1}]),
+                           ("n1m", [{}, {"lanes": 32}, {"no_linear": True}]), ("cfg3", [{}])):
+        c = big[name]
+        a = torch.from_numpy(rng.random_acgt(c["seed"], 0, c["n"]).copy()).cuda()
+        b = torch.from_numpy(rng.random_acgt(c["seed"], 1, c["m"]).copy()).cuda()
+        for kw in variants:
+            assert ctx.score_device(a.data_ptr(), c["n"], b.data_ptr(), c["m"], **kw) == c["score"], (name, kw)
+    ctx.close()
+
+
+def test_size_independent_properties_at_config3_size(api):
+    """4 M-base analytic cases: identical sequences, one planted 7-base deletion, disjoint alphabets."""
+    import torch
+    n = 4000000
+    ctx = api.Context(0)
+    a = rng.random_acgt(541, 0, n)
+    ta = torch.from_numpy(a.copy()).cuda()
+    assert ctx.score_device(ta.data_ptr(), n, ta.data_ptr(), n) == n                      # identical -> MATCH*N (far beyond s16)
+    b = np.concatenate([a[:2000000], a[2000007:]])                                        # 7 deleted bases: one gap of 7
+    tb = torch.from_numpy(b.copy()).cuda()
+    assert ctx.score_device(ta.data_ptr(), n, tb.data_ptr(), n - 7) == (n - 7) - (1 + 6 * 1)
+    x = torch.full((n,), ord("A"), dtype=torch.uint8, device="cuda"); y = torch.full((n,), ord("C"), dtype=torch.uint8, device="cuda")
+    assert ctx.score_device(x.data_ptr(), n, y.data_ptr(), n) == 0                        # disjoint alphabets -> 0
+    ctx.close()
 
 
 def _read_pairs(seed, npairs, read_len=150, win_len=1000):

@@ -40,8 +40,21 @@ class FakeRing:
     def connect_local(self, other):
         self.next = other.rank
 
+    def connect_root_ipc(self, h):
+        self.root = int(h[4:6])
+
+    def combine_pending(self):
+        return self.two_sided            # same on every rank, like the real plan
+
+    def combine(self, stream=0):
+        self.two_sided = False
+        return 7777 if self.rank == 0 else 0        # only the root holds the two middle rows
+
+    two_sided = False
+
     def partial(self, d1, n, d2, m, params, *, lanes, rebase=0, stream=0, **kw):
         FakeRing.log.append((lanes, rebase))
+        self.two_sided = n == 55                    # n == 55: a pair the plan sweeps from both ends; its best alignment crosses the middle
         true_score = 40000 if n == 99 else 1234          # n == 99: a pair whose score leaves the s16 range
         if lanes == 16 and rebase < 0 and true_score > 32000:
             return (32700, 1) if self.rank == 1 else (17, 0)     # only ONE rank notices the overflow
@@ -60,6 +73,8 @@ def _worker(rank, world, port, q):
     al = DistributedRingAligner(0, 1000, _ctx_factory=FakeCtx, _ring_factory=FakeRing)
     out = {"rank": rank, "next": al.ring.next}
     out["plain"] = al.score(0, 10, 0, 10)
+    out["root"] = al.ring.root
+    out["crossing"] = al.score(0, 55, 0, 55)
     FakeRing.log.clear()
     out["overflow"] = al.score(0, 99, 0, 99)
     out["widths"] = list(FakeRing.log)
@@ -86,6 +101,8 @@ def test_ring_orchestration_two_ranks_gloo():
         assert p.exitcode == 0
     assert [r["next"] for r in res] == [1, 0]                       # each rank mapped its successor's buffer
     assert [r["plain"] for r in res] == [1234, 1234]                # max over partial scores, same on every rank
+    assert [r["root"] for r in res] == [0, 0]                       # every rank mapped rank 0's region (two-sided sweeps)
+    assert [r["crossing"] for r in res] == [7777, 7777]             # rank 0's combination result reaches every rank
     assert [r["overflow"] for r in res] == [40000, 40000]           # every rank repeated the call ...
     assert [r["widths"] for r in res] == [[(16, -1), (16, 1)]] * 2       # ... (re-based lanes) although only rank 1 saw the overflow
     assert all("16-bit" in r["forced16"] for r in res)
