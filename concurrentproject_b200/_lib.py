@@ -59,6 +59,10 @@ EXPORTS = {
                            C.POINTER(C.c_longlong)], C.c_int),
     "swb200_score_span_device": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(Params),
                                   C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)], C.c_int),
+    "swb200_align": ([U8P, C.c_longlong, U8P, C.c_longlong, C.POINTER(Params), C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                      C.c_char_p, C.c_longlong, C.POINTER(C.c_longlong)], C.c_int),
+    "swb200_align_device": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(Params), C.c_void_p,
+                             C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.c_char_p, C.c_longlong, C.POINTER(C.c_longlong)], C.c_int),
     "swb200_last_run": ([C.c_void_p, C.POINTER(RunInfo)], C.c_int),
     "swb200_score_batch": ([U8P, C.POINTER(C.c_longlong), C.POINTER(C.c_int), U8P, C.POINTER(C.c_longlong), C.POINTER(C.c_int),
                             C.c_longlong, C.POINTER(Params), C.POINTER(Options), C.POINTER(C.c_int)], C.c_int),

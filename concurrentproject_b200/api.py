@@ -317,3 +317,23 @@ def set_devices(count: int) -> None:
 
 def get_devices() -> int:
     return int(_lib.load().swb200_get_devices())
+
+
+def align(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS):
+    """(score, (i_start, j_start, i_end, j_end), cigar): the best local alignment itself (swb200_align).  The extended
+    CIGAR reads from the start cell: '=' match, 'X' mismatch, 'I' a base of seq1 against a gap, 'D' a base of seq2 against
+    a gap; re-scored with MATCH / MISMATCH / G_INIT + (k-1) G_EXT per gap of length k it gives the score."""
+    a, b = _u8(seq1), _u8(seq2)
+    out, need = C.c_int(0), C.c_longlong(0)
+    span = (C.c_longlong * 4)()
+    p = _params(params)
+    cap = 64
+    while True:
+        buf = C.create_string_buffer(cap)
+        rc = _lib.load().swb200_align(_ptr(a), len(a), _ptr(b), len(b), C.byref(p), C.byref(out), span, buf, cap, C.byref(need))
+        if rc == -2 and need.value + 1 > cap:            # buffer too small: the call says how much it needs
+            cap = need.value + 1
+            continue
+        if rc != 0:
+            raise SwbError(rc, "swb200_align")
+        return out.value, tuple(int(x) for x in span), buf.value.decode()

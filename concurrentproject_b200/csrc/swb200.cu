@@ -245,11 +245,14 @@ struct swb200_ctx {
   uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
   unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
   int* d_cand = nullptr; size_t cand_cap = 0;     // end-cell tracking: {H, T position, Q row} per band
+  uint32_t* d_dirs = nullptr; size_t dirs_cap = 0;   // traceback directions (swb200_align): 4 bits per cell of the span rectangle
+  unsigned long long* d_ops = nullptr; size_t ops_cap = 0;   // run-length alignment operations, last operation first
   uint8_t* d_rev = nullptr; size_t rev_cap = 0;   // start-cell pass: the two reversed prefixes
   int* d_result = nullptr;        // [0] score [1] status, [2..9] presence bitmap
   uint8_t* d_lut = nullptr;       // 256 bytes
   int* h_result = nullptr;        // pinned
   unsigned epoch = 0;
+  long long last_nsteps = 0; int last_skew_per_lane = 0;     // geometry of the last engine run (the traceback walk needs it)
   swb200_run_info info{};
   long long* d_prof = nullptr; size_t prof_cap = 0;   // SWB200_PROF counters (grow-only, owned by the context)
   // grow-only staging of the host batch entry points (no cudaMalloc/cudaFree per call)
@@ -368,6 +371,43 @@ __global__ void reduce_end_kernel(const int* cand, int nb, int* out3) {
   if (threadIdx.x == 0) { out3[0] = sh[0]; out3[1] = sp[0]; out3[2] = sr[0]; }
 }
 
+// Traceback walk (swb200_align): follows the 4-bit directions the DIRS kernel recorded from the last cell of the span
+// rectangle back to its first.  One thread: the walk is a chain of dependent loads, at most rows + cols of them.
+// Operations come out last-first, run-length encoded: ops[k] = op << 56 | count, op 'M' (one column of seq1 against one
+// row of seq2), 'I' (a column of seq1 against a gap), 'D' (a row of seq2 against a gap).  Three states as in Gotoh's
+// traceback: in H the cell says diagonal / E / F; in E (F) the cell says whether the gap was extended or opened.
+__global__ void walk_traceback_kernel(const uint32_t* __restrict__ dirs, long long nsteps, int sk, long long rows, long long cols,
+                                      unsigned long long* ops, long long ops_cap, long long* n_ops_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long i = rows, j = cols, nops = 0, run = 0;
+  unsigned cur = 0;
+  int state = 0;
+  auto emit = [&](unsigned op, long long cnt) {
+    if (op == cur) { run += cnt; return; }
+    if (run > 0) { if (nops < ops_cap) ops[nops] = ((unsigned long long)cur << 56) | (unsigned long long)run; ++nops; }
+    cur = op; run = cnt;
+  };
+  while (i > 0 && j > 0) {
+    const long long r0 = i - 1;
+    const long long band = r0 >> 8;                       // 32 lanes x 8 rows per band
+    const int lane = (int)((r0 & 255) >> 3), r = (int)(r0 & 7);
+    const long long k = (j - 1) + (long long)sk * lane;   // the step at which this lane processed column j
+    const uint32_t d = (dirs[(size_t)(band * nsteps + k) * 32 + lane] >> (4 * r)) & 0xFu;
+    if (state == 0) {
+      const uint32_t src = d & 3u;
+      if (src == 0) { emit('M', 1); --i; --j; } else state = (int)src;
+    } else if (state == 1) {
+      emit('I', 1); state = (d & 4u) ? 1 : 0; --j;
+    } else {
+      emit('D', 1); state = (d & 8u) ? 2 : 0; --i;
+    }
+  }
+  if (j > 0) emit('I', j);
+  if (i > 0) emit('D', i);
+  emit(0, 0);                                             // flush the last run
+  *n_ops_out = nops;
+}
+
 struct Plan {
   int mode;      // 0 s16 affine, 1 s16 linear, 2 s32 affine, 3/4 = 0/1 with re-based lanes, 5 s32 bytes, 6/7 = 2/5 + end cell
   int R, config, ctas;
@@ -421,6 +461,12 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   if (lanes == 35) pl.mode = 7;          // the same for any byte alphabet
   if (lanes == 36) pl.mode = 8;          // anchored recurrence + position of the maximum (start-cell pass)
   if (lanes == 37) pl.mode = 9;
+  if (lanes == 38) pl.mode = 10;         // anchored recurrence + traceback directions (swb200_align)
+  if (lanes == 39) pl.mode = 11;
+  if (pl.mode >= 10) {                   // one kernel shape: 8 rows per lane (one direction word per step)
+    pl.R = 8; pl.config = o.config == 3 ? 3 : 1; pl.two_sided = false; pl.ctas = o.ctas;
+    return pl;
+  }
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
@@ -457,6 +503,8 @@ const void* kernel_for(const Plan& pl) {
     case 7: return swb::engine_kernel_mode7(pl.R, pl.config);
     case 8: return swb::engine_kernel_mode8(pl.R, pl.config);
     case 9: return swb::engine_kernel_mode9(pl.R, pl.config);
+    case 10: return swb::engine_kernel_mode10(pl.R, pl.config);
+    case 11: return swb::engine_kernel_mode11(pl.R, pl.config);
     default: return swb::engine_kernel_mode5(pl.R, pl.config);
   }
 }
@@ -536,7 +584,17 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
   } else if ((rc = grow(c->d_ext, c->ext_cap, ext_need, true, s))) return rc;
   if ((rc = grow(c->d_progress, c->progress_cap, (size_t)warps + 4, false, s))) return rc;
-  const bool track = pl.mode >= 6;
+  const bool dirs = pl.mode >= 10;
+  if (dirs) {
+    if (ring) return fail(SWB200_ERR_ARG, "traceback runs on one GPU through swb200_align");
+    const size_t words = (size_t)NB * (size_t)nsteps * 32;
+    size_t free_b = 0, total_b = 0;
+    SWB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (words > c->dirs_cap && words * sizeof(uint32_t) + (1ull << 30) > free_b + c->dirs_cap * sizeof(uint32_t))
+      return fail(SWB200_ERR_NOMEM, "the traceback matrix of this alignment (" + std::to_string(words * 4 >> 20) + " MiB) does not fit in device memory");
+    if ((rc = grow(c->d_dirs, c->dirs_cap, words, false, s))) return rc;
+  }
+  const bool track = pl.mode >= 6 && pl.mode <= 9;
   if (track && (ring || !end3)) return fail(SWB200_ERR_ARG, "end-cell tracking runs on one GPU through swb200_score_end");
   if (track && (rc = grow(c->d_cand, c->cand_cap, 3 * (size_t)NB + 3, false, s))) return rc;
 
@@ -550,7 +608,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
   SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
 
-  const bool generic = pl.mode == 5 || pl.mode == 7 || pl.mode == 9;       // raw bytes straight from the caller's buffers, nothing to encode
+  const bool generic = pl.mode == 5 || pl.mode == 7 || pl.mode == 9 || pl.mode == 11;       // raw bytes straight from the caller's buffers, nothing to encode
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
   const int tb = (int)std::min<long long>(std::max<long long>((LT / 32) / 256, 1), 4LL * c->sms);
   if (!generic) {
@@ -590,6 +648,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   }
   P.prof = d_prof;
   P.cand = track ? c->d_cand : nullptr;
+  P.dirs = dirs ? c->d_dirs : nullptr;
   L.split = split;
   // the two middle boundary rows of a two-sided sweep: local buffer, or the root rank's region on a ring
   uint2* final_f = ring ? ring->root + 4 * ring->len : c->d_final;
@@ -674,6 +733,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   c->info.rows = pl.R; c->info.config = pl.config;
   c->info.ctas = (int)ctas; c->info.warps = warps; c->info.bands = (int)NB; c->info.engine_launches += 1;
   c->info.engine_ms = ms;
+  c->last_nsteps = nsteps; c->last_skew_per_lane = swb::mode_is_s32(pl.mode) ? 1 + slack : 0;
   return SWB200_OK;
 }
 
@@ -683,10 +743,10 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
 // score 0.  Runs the 32-bit tracking kernel with seq2 striped and seq1 streamed, whatever the options say.
 int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
                         const swb200_params* pp, const swb200_options* oo, cudaStream_t s, int* score_out,
-                        long long* end_out = nullptr, bool anchored = false) {
+                        long long* end_out = nullptr, bool anchored = false, bool record_dirs = false) {
   const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
   swb200_options o = oo ? *oo : swb200_options{};
-  if (end_out) { o.orient = 2; o.lanes = 0; o.two_sided = -1; o.rebase = -1; if (o.rows > 16) o.rows = 16; }
+  if (end_out || record_dirs) { o.orient = 2; o.lanes = 0; o.two_sided = -1; o.rebase = -1; if (o.rows > 16) o.rows = 16; }
   int rc;
   if ((rc = check_params(p))) return rc;
   if (n < 0 || m < 0 || !score_out) return fail(SWB200_ERR_ARG, "negative length or null output");
@@ -710,6 +770,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
   int lanes = o.lanes == 32 ? 32 : 16;
   if (o.lanes != 32 && rb_ok && (o.rebase > 0 || bound > 8LL * 32767)) lanes = 17;
   if (end_out) lanes = anchored ? 36 : 34;
+  if (record_dirs) lanes = 38;           // anchored + traceback directions; seq2 striped, seq1 streamed (o.orient = 2 from the caller)
   int end3[3] = {0, 0, 0};
   // a score can never exceed match*min(n,m): skip the 16-bit attempt when it cannot fit anyway?  No:
   // random DNA scores ~0.11*N, so 16-bit lanes are right far beyond N = 32767; the engine reports
@@ -718,7 +779,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
     int score = 0, status = 0;
     if ((rc = run_once(c, d_seq1, n, d_seq2, m, p, o, lanes, lut, s, &score, &status, nullptr, end_out ? end3 : nullptr))) return rc;
     if (status & swb::STATUS_SPIN_TIMEOUT) return fail(SWB200_ERR_TIMEOUT, "boundary hand-off timed out");
-    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33 && lanes != 35 && lanes != 37) {
+    if ((status & swb::STATUS_BAD_SYMBOL) && lanes != 33 && lanes != 35 && lanes != 37 && lanes != 39) {
       if (lut) return fail(SWB200_ERR_ALPHABET, "internal: remapped symbols still out of range");
       // bytes other than A,C,G,T: remap the (at most 4) distinct values that occur
       SWB_CUDA(cudaMemsetAsync(c->d_result + 16, 0, 8 * sizeof(int), s));
@@ -737,7 +798,7 @@ int score_device_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const
         }
       if (distinct > 4) {
         // the reference compares raw bytes (main.cpp:28-33): score such pairs with the byte-compare kernel
-        lanes = end_out ? (anchored ? 37 : 35) : 33;
+        lanes = record_dirs ? 39 : (end_out ? (anchored ? 37 : 35) : 33);
         continue;
       }
       SWB_CUDA(cudaMemcpyAsync(c->d_lut, table, 256, cudaMemcpyHostToDevice, s));
@@ -869,7 +930,7 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   DeviceGuard guard;
   cudaSetDevice(c->device);
   cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
-  cudaFree(c->d_prof); cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
+  cudaFree(c->d_dirs); cudaFree(c->d_ops); cudaFree(c->d_prof); cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);
   if (c->h_result) cudaFreeHost(c->h_result);
@@ -1007,6 +1068,117 @@ int swb200_score_span(const unsigned char* seq1, long long n, const unsigned cha
   SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
   SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
   return score_span_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, s, score_out, span_out);
+}
+
+// Score, span and the alignment itself.  Pass 1 + 2: swb200_score_span (end cell, start cell).  Pass 3: the anchored
+// recurrence over the span rectangle with direction recording (modes 10/11), whose last cell must hold the score again;
+// then the walk.  The CIGAR is checked by re-scoring it with the costs of main.cpp:28-33,57-58 before it is returned.
+static int align_locked(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d_seq2, long long m,
+                        const swb200_params* pp, cudaStream_t s, int* score_out, long long* span4, std::string* cigar) {
+  cigar->clear();
+  int rc = score_span_locked(c, d_seq1, n, d_seq2, m, pp, s, score_out, span4);
+  if (rc || *score_out <= 0) return rc;
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  const long long is = span4[0], js = span4[1], ie = span4[2], je = span4[3];
+  const long long rows = ie - is + 1, cols = je - js + 1;
+  const swb200_run_info before = c->info;
+  int score3 = 0;
+  if ((rc = score_device_locked(c, d_seq1 + (js - 1), cols, d_seq2 + (is - 1), rows, pp, nullptr, s, &score3, nullptr, true, true))) return rc;
+  if (score3 != *score_out) return fail(SWB200_ERR_CUDA, "internal: the traceback pass does not reproduce the score");
+  const long long nsteps = c->last_nsteps;
+  const int sk = c->last_skew_per_lane;
+  const size_t cap = (size_t)(rows + cols + 4);
+  if ((rc = grow(c->d_ops, c->ops_cap, cap + 1, false, s))) return rc;
+  walk_traceback_kernel<<<1, 32, 0, s>>>(c->d_dirs, nsteps, sk, rows, cols, c->d_ops + 1, (long long)cap,
+                                         reinterpret_cast<long long*>(c->d_ops));
+  SWB_CUDA(cudaGetLastError());
+  long long nops = 0;
+  SWB_CUDA(cudaMemcpyAsync(&nops, c->d_ops, sizeof nops, cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaStreamSynchronize(s));
+  if (nops < 0 || (size_t)nops > cap) return fail(SWB200_ERR_CUDA, "internal: traceback walk overflowed its buffer");
+  std::vector<unsigned long long> ops((size_t)nops);
+  std::vector<uint8_t> a((size_t)cols), b((size_t)rows);
+  if (nops) SWB_CUDA(cudaMemcpyAsync(ops.data(), c->d_ops + 1, (size_t)nops * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaMemcpyAsync(a.data(), d_seq1 + (js - 1), (size_t)cols, cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaMemcpyAsync(b.data(), d_seq2 + (is - 1), (size_t)rows, cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaStreamSynchronize(s));
+  // forward order, 'M' split into '=' / 'X', re-scored on the way
+  long long i = 0, j = 0, total = 0;
+  char last = 0; long long run = 0;
+  auto put = [&](char op) {
+    if (op == last) { ++run; return; }
+    if (run) { *cigar += std::to_string(run); *cigar += last; }
+    last = op; run = 1;
+  };
+  for (long long k = nops - 1; k >= 0; --k) {
+    const char op = (char)(ops[(size_t)k] >> 56);
+    const long long cnt = (long long)(ops[(size_t)k] & 0x00FFFFFFFFFFFFFFull);
+    if (op == 'M') {
+      for (long long t = 0; t < cnt; ++t, ++i, ++j) {
+        if (i >= rows || j >= cols) return fail(SWB200_ERR_CUDA, "internal: traceback leaves the span");
+        const bool eq = a[(size_t)j] == b[(size_t)i];
+        total += eq ? p.match : p.mismatch;
+        put(eq ? '=' : 'X');
+      }
+    } else if (op == 'I' || op == 'D') {
+      total -= p.gap_init + (cnt - 1) * (long long)p.gap_ext;          // main.cpp:57-58: first gap character costs G_INIT
+      for (long long t = 0; t < cnt; ++t) put(op);
+      if (op == 'I') j += cnt; else i += cnt;
+    } else return fail(SWB200_ERR_CUDA, "internal: unknown traceback operation");
+  }
+  put(0);
+  if (i != rows || j != cols || total != *score_out)
+    return fail(SWB200_ERR_CUDA, "internal: the alignment does not re-score to the score (" + std::to_string(total) + " vs " + std::to_string(*score_out) + ")");
+  c->info.engine_launches += before.engine_launches; c->info.aux_launches += before.aux_launches + 1;
+  c->info.engine_ms += before.engine_ms; c->info.cells += before.cells;
+  return SWB200_OK;
+}
+
+static int align_finish(const std::string& cigar, char* cigar_out, long long cigar_cap, long long* cigar_len_out) {
+  if (cigar_len_out) *cigar_len_out = (long long)cigar.size();
+  if (!cigar_out) return SWB200_OK;                          // length query
+  if (cigar_cap < (long long)cigar.size() + 1) return fail(SWB200_ERR_ARG, "cigar buffer too small (see cigar_len_out)");
+  memcpy(cigar_out, cigar.c_str(), cigar.size() + 1);
+  return SWB200_OK;
+}
+
+int swb200_align_device(swb200_ctx* c, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2, long long m,
+                        const swb200_params* p, void* stream, int* score_out, long long span_out[4], char* cigar_out,
+                        long long cigar_cap, long long* cigar_len_out) {
+  if (!c || !span_out || !score_out) return fail(SWB200_ERR_ARG, "null context or output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::string cigar;
+  const int rc = align_locked(c, d_seq1, n, d_seq2, m, p, (cudaStream_t)stream, score_out, span_out, &cigar);
+  if (rc) return rc;
+  return align_finish(cigar, cigar_out, cigar_cap, cigar_len_out);
+}
+
+int swb200_align(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m, const swb200_params* p,
+                 int* score_out, long long span_out[4], char* cigar_out, long long cigar_cap, long long* cigar_len_out) {
+  if (n < 0 || m < 0 || !score_out || !span_out || (n > 0 && !seq1) || (m > 0 && !seq2))
+    return fail(SWB200_ERR_ARG, "bad sequence arguments");
+  span_out[0] = span_out[1] = span_out[2] = span_out[3] = 0;
+  if (cigar_len_out) *cigar_len_out = 0;
+  if (cigar_out && cigar_cap > 0) cigar_out[0] = 0;
+  if (n == 0 || m == 0) {
+    if (p) { int rc = check_params(*p); if (rc) return rc; }
+    *score_out = 0;
+    return SWB200_OK;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->own_stream;
+  const size_t off2 = ((size_t)n + 255) & ~(size_t)255;
+  if ((rc = grow(c->d_ascii, c->ascii_cap, off2 + (size_t)m + 256, false, s))) return rc;
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii, seq1, (size_t)n, cudaMemcpyHostToDevice, s));
+  SWB_CUDA(cudaMemcpyAsync(c->d_ascii + off2, seq2, (size_t)m, cudaMemcpyHostToDevice, s));
+  std::string cigar;
+  if ((rc = align_locked(c, c->d_ascii, n, c->d_ascii + off2, m, p, s, score_out, span_out, &cigar))) return rc;
+  return align_finish(cigar, cigar_out, cigar_cap, cigar_len_out);
 }
 
 int swb200_score(const unsigned char* seq1, int n, const unsigned char* seq2, int m, const swb200_params* p,

@@ -75,6 +75,8 @@ struct EngineParams {
   long long* prof;              // optional [warps_local][8]: cycles in prologue, cycles in steps, failed polls, chunks,
                                 //   globaltimer at the first band's first chunk / at its end, SM id
   int* cand;                    // TRACK kernels: per band {best H, its T position, its Q row} (first in column-major order)
+  uint32_t* dirs;               // DIRS kernels: traceback directions, 4 bits per cell, word (band * nsteps + step) * 32 + lane,
+                                //   nibble r = row r of the lane: bits 0-1 where H came from (0 diagonal, 1 E, 2 F), bit 2 E extended, bit 3 F extended
 };
 
 struct WarpSmem {
@@ -585,8 +587,13 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 //  is that alignment's START cell.  Only lane 0 of a band starts with the column-0 border in its registers; the
 //  other lanes start at -inf (they are still left of column 0) and build column 0 from the F values arriving from
 //  above, which is exactly the recurrence of that column.
-template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = false, bool ANCH = false>
+//  DIRS (with ANCH, round 2): also record, for every cell, where its H, E and F came from (4 bits per cell, one 32-bit
+//  word per lane and step for R = 8) -- the traceback matrix of the GLOBAL alignment between the start and the end
+//  cell that swb200_score_span found; walk_traceback_kernel (swb200.cu) follows it back.  Uses the plain row loop
+//  (E and F exactly as in main.cpp:57-58, no short-chain rewriting), so the flags mean what they say.
+template <int R, int SLACK, bool GEN = false, bool SHORT = true, bool TRACK = false, bool ANCH = false, bool DIRS = false>
 SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
+  static_assert(!DIRS || (ANCH && !SHORT && !TRACK && R <= 8), "direction recording: anchored recurrence, plain row loop, 8 rows per lane");
   constexpr int SK = 1 + SLACK;
   constexpr int SKEW = 31 * SK;
   constexpr int kU = step_unroll(8.0, R, kStepUnroll32);
@@ -777,20 +784,28 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
           }
         } else {
           int Hup = upHo;
+          uint32_t dword = 0;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int s = GEN ? (sel[r] == Tw ? s_match : s_mismatch) : (int)prmt(Tw, 0u, sel[r]);
             const int d = diag + s;
             const int old = Ho[r];
+            const int e_ext = E[r] + next, f_ext = F + next;
             E[r] = addmax32(E[r], next, old);
             F = addmax32(F, next, Hup);
             const int h = ANCH ? max3_32(d, E[r], F) : max3relu32(d, E[r], F);
+            if (DIRS) {
+              // ties: diagonal before E before F; a gap counts as extended only if extending is strictly better
+              const uint32_t src = h == d ? 0u : (h == E[r] ? 1u : 2u);
+              dword |= (src | (e_ext > old ? 4u : 0u) | (f_ext > Hup ? 8u : 0u)) << (4 * r);
+            }
             Ho[r] = h + nopen;
             Hup = Ho[r];
             diag = old;
             if (TRACK) { const int key = (ANCH ? (h > 0 ? h : 0) : h) * 2048 + (cstep - r); bestkey = bestkey > key ? bestkey : key; }
             else if (r & 1) best1 = best1 > h ? best1 : h; else best0 = best0 > h ? best0 : h;
           }
+          if (DIRS) P.dirs[((size_t)band * (size_t)nsteps + (size_t)(i0 + k)) * 32 + lane] = dword;
         }
         if (TRACK) cstep -= 16;
         xsH = Ho[R - 1];
@@ -828,7 +843,7 @@ SWB_HD void engine_warp_s32(const EngineParams& P, const WarpCtx& w, int lw, War
 
 // rows of Q one band covers
 // modes 2, 5, 6, 7 run 32-bit lanes (6, 7 = 2, 5 with end-cell tracking)
-SWB_HD bool mode_is_s32(int mode) { return mode == 2 || mode >= 5; }      // 8, 9 = 6, 7 with the anchored recurrence
+SWB_HD bool mode_is_s32(int mode) { return mode == 2 || mode >= 5; }      // 8, 9 = 6, 7 with the anchored recurrence; 10, 11 = anchored + traceback directions
 SWB_HD int rows_per_band(int R, int mode) { return (mode_is_s32(mode) ? 32 : 64) * R; }
 
 }  // namespace swb

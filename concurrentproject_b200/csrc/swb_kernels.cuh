@@ -35,6 +35,8 @@ const void* engine_kernel_mode6(int R, int config);   // mode 2 + position of th
 const void* engine_kernel_mode7(int R, int config);   // mode 5 + position of the maximum
 const void* engine_kernel_mode8(int R, int config);   // mode 6 with the anchored recurrence (start cell, swb200_score_span)
 const void* engine_kernel_mode9(int R, int config);   // mode 7 with the anchored recurrence
+const void* engine_kernel_mode10(int R, int config);  // anchored recurrence + traceback directions (swb200_align); R = 8 only
+const void* engine_kernel_mode11(int R, int config);  // the same for any byte alphabet
 
 // One launch can carry two independent sub-problems (two-sided sweep): warps [0, split) run `a`, the rest run `b`,
 // each as its own ring with its own buffers.  split == 0: everything runs `a`.
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   else if constexpr (MODE == 7) engine_warp_s32<R, SLACK, true, SHORT, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 8) engine_warp_s32<R, SLACK, false, SHORT, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 9) engine_warp_s32<R, SLACK, true, SHORT, true, true>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 10) engine_warp_s32<R, SLACK, false, false, false, true, true>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE == 11) engine_warp_s32<R, SLACK, true, false, false, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT, HS>(P, w, lw, &sm[wi]);
   else engine_warp_s16<R, MODE, SLACK, false, SHORT, HS>(P, w, lw, &sm[wi]);
 }
@@ -78,9 +82,14 @@ static const void* engine_kernel_lookup(int R, int config) {
     return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
          : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \
                        : (const void*)sw_engine_kernel<RR, MODE, 0, 4>;
-  switch (R) {
-    SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(10) SWB_CASE(12) SWB_CASE(14) SWB_CASE(16)
-    default: return nullptr;
+  if constexpr (MODE == 10 || MODE == 11) {      // one shape only: 8 rows per lane = one 32-bit direction word per step
+    if (R != 8 || config == 2) return nullptr;
+    return config == 1 ? (const void*)sw_engine_kernel<8, MODE, 1, 4> : (const void*)sw_engine_kernel<8, MODE, 0, 4>;
+  } else {
+    switch (R) {
+      SWB_CASE(1) SWB_CASE(2) SWB_CASE(3) SWB_CASE(4) SWB_CASE(6) SWB_CASE(8) SWB_CASE(10) SWB_CASE(12) SWB_CASE(14) SWB_CASE(16)
+      default: return nullptr;
+    }
   }
 #undef SWB_CASE
 }

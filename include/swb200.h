@@ -124,6 +124,25 @@ SWB200_API int swb200_score_span_device(swb200_ctx* ctx, const unsigned char* d_
                              const unsigned char* d_seq2, long long m, const swb200_params* p, void* stream,
                              int* score_out, long long span_out[4]);
 
+/* ---- the alignment itself (second half; the reference is score-only, README.md:6) ----------
+ * Score, span (as swb200_score_span) and an extended CIGAR of the best local alignment between the start and the end
+ * cell, read from the start cell: "<count>=" matches, "<count>X" mismatches, "<count>I" bases of seq1 against a gap,
+ * "<count>D" bases of seq2 against a gap.  Contract: re-scoring the CIGAR over the span with the costs of
+ * main.cpp:28-33,57-58 (MATCH / MISMATCH per pair, G_INIT for the first character of a gap, G_EXT for each further
+ * one) gives exactly *score_out -- the library checks this itself before it returns.  Which of several equally good
+ * alignments is reported: at every cell diagonal before gap in seq2 (E) before gap in seq1 (F); a gap counts as
+ * extended only where extending is strictly better than opening.
+ * Three passes: end cell, start cell, then the anchored recurrence over the span rectangle with 4 bits of traceback
+ * direction per cell kept in HBM (0.5 byte per cell: the 100 000 x 100 000 pair takes 5 GB; SWB200_ERR_NOMEM when the
+ * rectangle does not fit) and a walk back through them.  cigar_out may be NULL to ask for the length only
+ * (*cigar_len_out, without the terminating NUL).  Same limits as swb200_score_end. */
+SWB200_API int swb200_align(const unsigned char* seq1, long long n, const unsigned char* seq2, long long m,
+                            const swb200_params* p, int* score_out, long long span_out[4], char* cigar_out,
+                            long long cigar_cap, long long* cigar_len_out);
+SWB200_API int swb200_align_device(swb200_ctx* ctx, const unsigned char* d_seq1, long long n, const unsigned char* d_seq2,
+                                   long long m, const swb200_params* p, void* stream, int* score_out, long long span_out[4],
+                                   char* cigar_out, long long cigar_cap, long long* cigar_len_out);
+
 /* What the last swb200_score*_ call on this context actually ran. */
 typedef struct {
   int lanes;            /* 16 or 32 */

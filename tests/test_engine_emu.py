@@ -178,3 +178,35 @@ def test_bottom_boundary_row_of_the_last_band(emu, mode, slack):
         if mode == 0:
             pos = (F[1:] > 0) | (hi > 0)           # non-positive F never matters and conventions differ at the border
             assert hi[pos].tolist() == F[1:][pos].tolist()
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+def test_rebasing_really_triggers(emu, mode):
+    """Re-based 16-bit lanes with scores far above the +-8000 trigger (score ~22 000 with match 10): every band re-centres
+    several times, publishes its bases in the link rings and translates what it receives; two emulated GPUs in the
+    second case.  (The small cases above never leave the first base.)"""
+    p = (10, -8, 10, 5) if mode == 3 else (10, -8, 7, 7)
+    for n, R, W, G in ((2500, 1, 3, 1), (3000, 2, 2, 2)):
+        a = rng.random_acgt(777 + n, 0, n)
+        b = rng.mutate(a, 777 + n, 1, 0.05, 0.02)
+        want = O.gotoh_rolling(a, b, p)
+        assert want > 20000
+        for slack in (1, 0):
+            assert emu(a, b, R, mode, slack, W, G, p) == (want, 0), (n, R, W, G, slack)
+
+
+@pytest.mark.parametrize("mode,slack", [(0, 1), (1, 1), (3, 1), (4, 0)])
+def test_slack_inside_a_thread(emu, mode, slack):
+    """Launch config 4 (HS 1): the hi sub-lane runs two T positions behind the lo sub-lane.  Same cases as the plain
+    engine, plus a re-basing one; the lane skew grows to 31*(3+slack)+2 and the table / bottom-row copies are one step
+    older, nothing else changes."""
+    lin = mode in (1, 4)
+    cases = [(300, 1, 2, 1, O.DEFAULT), (800, 2, 3, 2, (3, -2, 2, 2) if lin else (2, -3, 5, 1)), (1000, 4, 2, 1, (1, -3, 1, 1) if lin else (1, -1, 4, 2))]
+    for k, (n, R, W, G, p) in enumerate(cases):
+        a, b = planted(300 + k, n)
+        assert emu(a, b, R, mode, slack, W, G, p, hs=True) == (O.gotoh_rolling(a, b, p), 0), (n, R, W, G, p)
+    if mode >= 3:
+        p = (10, -8, 7, 7) if lin else (10, -8, 10, 5)
+        a = rng.random_acgt(3277, 0, 2500)
+        b = rng.mutate(a, 3277, 1, 0.05, 0.02)
+        assert emu(a, b, 1, mode, slack, 3, 1, p, hs=True) == (O.gotoh_rolling(a, b, p), 0)

@@ -152,3 +152,28 @@ def test_end_cell_and_span_oracles_are_self_consistent():
             assert O.gotoh_full(a[:je - 1], b, p) < s
         if ie > 1:
             assert O.gotoh_full(a[:je], b[:ie - 1], p) < s
+
+
+def test_fast_oracle_equals_the_rolling_row_oracle():
+    """oracle/gotoh_fast.c (one tile per SIMD lane; pins the scores under tests/golden/large_scores.json) against
+    oracle_gotoh_rolling on ragged tile edges, non-default parameters, and a pair larger than one tile diagonal."""
+    for (n, m, seed) in [(1, 1, 1), (3, 700, 2), (255, 257, 3), (256, 256, 4), (1000, 1000, 5), (5000, 3333, 6), (4097, 8191, 7)]:
+        a = rng.random_acgt(seed, 0, n)
+        b = rng.mutate(rng.random_acgt(seed, 0, m) if m <= n else rng.random_acgt(seed, 1, m), seed, 3, 0.1, 0.05)
+        for p in [(1, -1, 1, 1), (2, -3, 5, 1), (5, -4, 11, 1), (1, -1, 0, 0)]:
+            assert O.gotoh_fast(a, b, p) == O.gotoh_rolling(a, b, p), (n, m, p)
+    a = rng.random_acgt(11, 0, 30000)
+    b = rng.mutate(a, 11, 1, 0.15, 0.05)[:20001]
+    assert O.gotoh_fast(a, b) == O.gotoh_mt(a, b)
+    assert O.gotoh_fast(b"", b"ACGT") == 0
+
+
+def test_pinned_large_scores_file():
+    """The committed pins: cfg2 agrees with the unmodified reference's own LazySmith (ref_scores_default.json), the
+    small one is recomputed here."""
+    big = load_json("large_scores.json")
+    assert {"cfg2", "ring400k", "n1m", "cfg3"} <= set(big)
+    ref = [c for c in load_json("ref_scores_default.json") if c.get("config") == "cfg2"][0]
+    assert big["cfg2"]["score"] == ref["score"]
+    c = big["cfg2"]
+    assert O.gotoh_fast(rng.random_acgt(c["seed"], 0, c["n"]), rng.random_acgt(c["seed"], 1, c["m"])) == c["score"]
