@@ -337,3 +337,42 @@ def align(seq1: Bytes, seq2: Bytes, params: Sequence[int] = DEFAULT_PARAMS):
         if rc != 0:
             raise SwbError(rc, "swb200_align")
         return out.value, tuple(int(x) for x in span), buf.value.decode()
+
+
+def batch_strides(max_short: int, max_long: int) -> Tuple[int, int]:
+    qs, ts = C.c_longlong(0), C.c_longlong(0)
+    rc = _lib.load().swb200_batch_strides(max_short, max_long, C.byref(qs), C.byref(ts))
+    if rc != 0:
+        raise SwbError(rc, "swb200_batch_strides")
+    return qs.value, ts.value
+
+
+def pack_batch_host(flat1, off1, len1, flat2, off2, len2):
+    """Raw A,C,G,T bytes -> the resident 2-bit layout, on the host (swb200_pack_batch_host): (q_words, q_stride, t_words,
+    t_stride, q_len, t_len) as numpy arrays / ints, ready for score_batch_packed."""
+    n = len(len1)
+    short = np.minimum(len1, len2); long_ = np.maximum(len1, len2)
+    qs, ts = batch_strides(int(short.max()) if n else 0, int(long_.max()) if n else 0)
+    qw, tw = np.zeros(max(n, 1) * qs, dtype=np.uint64), np.zeros(max(n, 1) * ts, dtype=np.uint64)
+    ql, tl = np.zeros(max(n, 1), dtype=np.int32), np.zeros(max(n, 1), dtype=np.int32)
+    LL, I, U = C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)
+    rc = _lib.load().swb200_pack_batch_host(_ptr(flat1), off1.ctypes.data_as(LL), len1.ctypes.data_as(I), _ptr(flat2), off2.ctypes.data_as(LL),
+                                            len2.ctypes.data_as(I), n, qs, ts, qw.ctypes.data_as(U), tw.ctypes.data_as(U),
+                                            ql.ctypes.data_as(I), tl.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_pack_batch_host")
+    return qw, qs, tw, ts, ql, tl
+
+
+def score_batch_packed(qw: np.ndarray, q_stride: int, tw: np.ndarray, t_stride: int, ql: np.ndarray, tl: np.ndarray,
+                       params: Sequence[int] = DEFAULT_PARAMS, *, rows: int = 0, no_linear: bool = False) -> np.ndarray:
+    """swb200_score_batch_packed: HOST batches already in the 2-bit resident format (a quarter of the PCIe bytes)."""
+    n = len(ql)
+    out = np.zeros(n, dtype=np.int32)
+    p, o = _params(params), _options(rows=rows, no_linear=no_linear)
+    I, U = C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)
+    rc = _lib.load().swb200_score_batch_packed(qw.ctypes.data_as(U), q_stride, tw.ctypes.data_as(U), t_stride, ql.ctypes.data_as(I),
+                                               tl.ctypes.data_as(I), n, C.byref(p), C.byref(o), out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_batch_packed")
+    return out

@@ -1892,6 +1892,142 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
   return score_batch_host_ctx(c, seq1_all, off1, len1, seq2_all, off2, len2, npairs, p, opt, banded, band_lo, band_hi, scores_out);
 }
 
+// ---- host batches that are ALREADY in the resident 2-bit format: a quarter of the bytes over PCIe, no pack kernel ----
+static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_words, long long q_stride,
+                                  const unsigned long long* t_words, long long t_stride, const int* q_len, const int* t_len,
+                                  long long npairs, int max_short, int max_long, const swb200_params* p, const swb200_options* opt,
+                                  int* scores_out) {
+  if (npairs == 0) return SWB200_OK;
+  const swb200_params pv = p ? *p : swb200_params{1, -1, 1, 1};
+  const swb200_options ov = opt ? *opt : swb200_options{};
+  int rc;
+  if ((rc = check_params(pv))) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard guard;
+  SWB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t sc = c->own_stream, sk = c->aux_stream;
+  const size_t np = (size_t)npairs;
+  if ((rc = grow(c->hb_scores, c->hb_scores_cap, np, false, sc)) || (rc = grow(c->hb_qw, c->hb_qw_cap, np * q_stride, false, sc)) ||
+      (rc = grow(c->hb_tw, c->hb_tw_cap, np * t_stride, false, sc)) || (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, sc)) ||
+      (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, sc))) return rc;
+  const BatchView all{c->hb_qw, c->hb_tw, c->hb_ql, c->hb_tl, q_stride, t_stride, npairs, max_short, max_long};
+  if ((rc = check_batch_score(all, pv, 0))) return rc;
+  const long long forced = settings().batch_chunk_bytes;
+  const long long target = forced > 0 ? forced : 48LL << 20;
+  const long long per_pair = (q_stride + t_stride) * 8 + 8;
+  const long long chunk_pairs = std::max<long long>(forced > 0 ? 1 : 1024, target / per_pair);
+  const size_t nchunks = (size_t)((npairs + chunk_pairs - 1) / chunk_pairs);
+  while (c->chunk_events.size() < nchunks + 1) {
+    cudaEvent_t e;
+    SWB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->chunk_events.push_back(e);
+  }
+  c->info = swb200_run_info{};
+  for (long long k = 0; k < npairs; ++k) c->info.cells += (long long)q_len[k] * t_len[k];
+  bool first = true;
+  for (size_t ci = 0; ci < nchunks; ++ci) {
+    const long long k0 = (long long)ci * chunk_pairs, nk = std::min(chunk_pairs, npairs - k0);
+    SWB_CUDA(cudaMemcpyAsync(c->hb_qw + k0 * q_stride, q_words + k0 * q_stride, (size_t)(nk * q_stride) * 8, cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaMemcpyAsync(c->hb_tw + k0 * t_stride, t_words + k0 * t_stride, (size_t)(nk * t_stride) * 8, cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaMemcpyAsync(c->hb_ql + k0, q_len + k0, (size_t)nk * sizeof(int), cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaMemcpyAsync(c->hb_tl + k0, t_len + k0, (size_t)nk * sizeof(int), cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaEventRecord(c->chunk_events[ci], sc));
+    SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
+    if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
+    const BatchView v{c->hb_qw + k0 * q_stride, c->hb_tw + k0 * t_stride, c->hb_ql + k0, c->hb_tl + k0, q_stride, t_stride, nk, max_short, max_long};
+    if ((rc = launch_batch_score(c, v, pv, ov, sk, c->hb_scores + k0, &c->info))) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
+  }
+  SWB_CUDA(cudaEventRecord(c->ev1, sk));
+  SWB_CUDA(cudaMemcpyAsync(scores_out, c->hb_scores, npairs * sizeof(int), cudaMemcpyDeviceToHost, sk));
+  SWB_CUDA(cudaStreamSynchronize(sk));
+  SWB_CUDA(cudaStreamSynchronize(sc));
+  float ms = 0;
+  SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->info.engine_ms = ms;
+  return SWB200_OK;
+}
+
+extern "C" {
+
+int swb200_batch_strides(int max_short, int max_long, long long* q_stride, long long* t_stride) {
+  if (max_short < 0 || max_long < max_short || !q_stride || !t_stride) return fail(SWB200_ERR_ARG, "bad batch shape");
+  *q_stride = std::max(1, (max_short + 31) / 32);
+  *t_stride = std::max(1, (max_long + 31) / 32) + 2;      // +2: the kernel prefetches one word past the end
+  return SWB200_OK;
+}
+
+// Format conversion on the host (no scoring here): raw A,C,G,T bytes -> the resident 2-bit layout, shorter sequence of
+// each pair first.  Same words as the device packer (swb_batch.cu: pack_batch_kernel) produces.
+int swb200_pack_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                           const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
+                           unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len) {
+  if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !q_words || !t_words || !q_len || !t_len)))
+    return fail(SWB200_ERR_ARG, "bad batch arguments");
+  for (long long k = 0; k < npairs; ++k) {
+    const bool swap = len1[k] > len2[k];
+    const unsigned char* q = swap ? seq2_all + off2[k] : seq1_all + off1[k];
+    const unsigned char* t = swap ? seq1_all + off1[k] : seq2_all + off2[k];
+    const int lq = swap ? len2[k] : len1[k], lt = swap ? len1[k] : len2[k];
+    if (lq < 0 || (lq + 31) / 32 > q_stride || (lt + 31) / 32 + 2 > t_stride) return fail(SWB200_ERR_ARG, "pair longer than the strides allow");
+    for (int side = 0; side < 2; ++side) {
+      const unsigned char* src = side ? t : q;
+      const int len = side ? lt : lq;
+      unsigned long long* dst = side ? t_words + k * t_stride : q_words + k * q_stride;
+      const long long stride = side ? t_stride : q_stride;
+      for (long long w = 0; w < stride; ++w) {
+        unsigned long long out = 0;
+        for (int b = 0; b < 32 && w * 32 + b < len; ++b) {
+          const unsigned c = src[w * 32 + b], v = (c >> 1) & 3u;
+          if (c != ((0x47544341u >> (8 * v)) & 0xFFu)) return fail(SWB200_ERR_ALPHABET, "batch input contains bytes other than A,C,G,T");
+          out |= (unsigned long long)v << (2 * b);
+        }
+        dst[w] = out;
+      }
+    }
+    q_len[k] = lq; t_len[k] = lt;
+  }
+  return SWB200_OK;
+}
+
+int swb200_score_batch_packed(const unsigned long long* q_words, long long q_stride, const unsigned long long* t_words,
+                              long long t_stride, const int* q_len, const int* t_len, long long npairs,
+                              const swb200_params* p, const swb200_options* opt, int* scores_out) {
+  if (npairs < 0 || q_stride < 1 || t_stride < 3 || (npairs > 0 && (!q_words || !t_words || !q_len || !t_len || !scores_out)))
+    return fail(SWB200_ERR_ARG, "bad batch arguments");
+  if (npairs == 0) return SWB200_OK;
+  int max_short = 0, max_long = 0;
+  for (long long k = 0; k < npairs; ++k) {
+    if (q_len[k] < 0 || t_len[k] < q_len[k] || (q_len[k] + 31) / 32 > q_stride || (t_len[k] + 31) / 32 + 2 > t_stride)
+      return fail(SWB200_ERR_ARG, "pair lengths do not fit the strides (q must be the shorter sequence)");
+    max_short = std::max(max_short, q_len[k]); max_long = std::max(max_long, t_len[k]);
+  }
+  {
+    std::unique_lock<std::mutex> pl(g_pool.mu);
+    const int G = (int)g_pool.ctx.size();
+    if (G > 1 && npairs >= 2LL * G) {
+      const long long per = (npairs + G - 1) / G;
+      int rc = pool_parallel(G, [&](int g) -> int {
+        const long long k0 = std::min<long long>(npairs, (long long)g * per), k1 = std::min<long long>(npairs, k0 + per);
+        return score_batch_packed_ctx(g_pool.ctx[(size_t)g], q_words + k0 * q_stride, q_stride, t_words + k0 * t_stride, t_stride, q_len + k0,
+                                      t_len + k0, k1 - k0, max_short, max_long, p, opt, scores_out + k0);
+      });
+      if (rc) return rc;
+      g_pool.info = g_pool.ctx[0]->info;
+      g_pool.info.cells = 0; g_pool.info.engine_ms = 0;
+      for (int g = 0; g < G; ++g) { g_pool.info.cells += g_pool.ctx[(size_t)g]->info.cells; g_pool.info.engine_ms = std::max(g_pool.info.engine_ms, g_pool.ctx[(size_t)g]->info.engine_ms); }
+      g_pool.info_valid = true;
+      return SWB200_OK;
+    }
+    g_pool.info_valid = false;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  return score_batch_packed_ctx(c, q_words, q_stride, t_words, t_stride, q_len, t_len, npairs, max_short, max_long, p, opt, scores_out);
+}
+
+}  // extern "C"
+
 static bool pool_last_run(swb200_run_info* info) {
   std::lock_guard<std::mutex> pl(g_pool.mu);
   if (!g_pool.info_valid) return false;

@@ -103,15 +103,17 @@ class Bucket:
     index: np.ndarray    # pair ids, in the order they are handed to the kernel
 
 
-def plan_buckets(len1: np.ndarray, len2: np.ndarray, acgt_only: np.ndarray, min_bucket: int = 512) -> List[Bucket]:
+def plan_buckets(len1: np.ndarray, len2: np.ndarray, acgt_only: np.ndarray, min_bucket: int = 512, match: int = 1) -> List[Bucket]:
     """Partition pair ids.  Batch buckets are keyed by the capacity class of min(len1, len2); a class with fewer
     than ``min_bucket`` pairs is merged into the next larger one (a launch costs more than the padding).  Inside a
-    bucket pairs are ordered by max(len1, len2), longest first."""
+    bucket pairs are ordered by max(len1, len2), longest first.  Pairs the 16-bit batch kernel cannot hold
+    (match * min(len) > 32766 - match, swb200.cu: check_batch_score) go to the single-pair engine, which re-runs in
+    re-based or 32-bit lanes by itself."""
     len1 = np.asarray(len1, dtype=np.int64)
     len2 = np.asarray(len2, dtype=np.int64)
     short = np.minimum(len1, len2)
     long_ = np.maximum(len1, len2)
-    batchable = np.asarray(acgt_only, dtype=bool) & (short <= BATCH_MAX_SHORT)
+    batchable = np.asarray(acgt_only, dtype=bool) & (short <= BATCH_MAX_SHORT) & (int(match) * short <= 32766 - int(match))
     out: List[Bucket] = []
     edges = np.array(BUCKET_EDGES)
     cls = np.searchsorted(edges, short, side="left")          # first edge >= short
@@ -191,7 +193,7 @@ def score_records(a: FastaRecords, ia: np.ndarray, b: FastaRecords, ib: np.ndarr
         fb, ok_b = (fa, ok_a) if b is a else _device_records(b, torch, dev)
         l1, l2 = a.lengths[ia].astype(np.int32), b.lengths[ib].astype(np.int32)
         o1, o2 = a.offsets[ia].astype(np.int64), b.offsets[ib].astype(np.int64)
-        buckets = plan_buckets(l1, l2, ok_a[ia] & ok_b[ib], min_bucket)
+        buckets = plan_buckets(l1, l2, ok_a[ia] & ok_b[ib], min_bucket, match=int(params[0]))
         stream = torch.cuda.current_stream(dev).cuda_stream
         for bk in buckets:
             ids = bk.index

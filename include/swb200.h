@@ -39,8 +39,9 @@ typedef struct {
 /* Kernel selection; all zero = automatic.  Exposed for benchmarking and tests. */
 typedef struct {
   int lanes;       /* 0 auto (packed 16-bit, 32-bit re-run if the score leaves the s16 range), 16, 32 */
-  int rows;        /* R: DP rows per sub-lane, one of 1,2,3,4,6,8,12,16; 0 auto */
-  int config;      /* 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA) */
+  int rows;        /* R: DP rows per sub-lane, one of 1,2,3,4,6,8,10,12,14,16 (batch kernel: 2,4,6,8,10,12,16); 0 auto */
+  int config;      /* 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA), 3 = one, no slack step,
+                      4 = 1 plus a slack step inside each thread (16-bit lanes only; measurement variant) */
   int ctas;        /* thread blocks (<= co-resident limit); 0 auto */
   int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
   int orient;      /* 0 auto (stripe the longer sequence across lanes), 1 = stripe seq1, 2 = stripe seq2 */
@@ -164,12 +165,27 @@ SWB200_API int swb200_last_run(swb200_ctx* ctx, swb200_run_info* info);
  * The reference scores pairs one call at a time (TestFileWithGPU.cpp:57-94); a batch call scores
  * npairs independent pairs in one kernel, several pairs per warp, nothing leaving the registers.
  * Pair k is seq1_all[off1[k] .. off1[k]+len1[k]) vs seq2_all[off2[k] .. off2[k]+len2[k]).
- * Limits: bytes must be A,C,G,T; min(len1[k], len2[k]) <= 1024 and match*min(len) <= 32766 for every
- * pair (longer pairs: swb200_score).  Empty sequences score 0. */
+ * Limits: bytes must be A,C,G,T; min(len1[k], len2[k]) <= 1024 and match*min(len) <= 32766 - match for every
+ * pair (SWB200_ERR_RANGE otherwise; such pairs: swb200_score).  Empty sequences score 0. */
 SWB200_API int swb200_score_batch(const unsigned char* seq1_all, const long long* off1, const int* len1,
                                   const unsigned char* seq2_all, const long long* off2, const int* len2,
                                   long long npairs, const swb200_params* p, const swb200_options* opt,
                                   int* scores_out);
+
+/* The same for HOST batches that are already in the resident 2-bit format (32 symbols per 64-bit word, symbol k at bits
+ * 2*(k%32), codes (c >> 1) & 3, i.e. A,C,G,T -> 0,1,3,2; per pair q_stride words of the SHORTER sequence and t_stride words
+ * of the longer one; strides from swb200_batch_strides): a quarter of the bytes cross PCIe and no pack kernel runs.
+ * swb200_pack_batch_host converts raw bytes into that layout on the host (format conversion only -- nothing is scored on
+ * the CPU); it writes the same words as the device packer.  q_len / t_len: the packed lengths (q_len[k] <= t_len[k]). */
+SWB200_API int swb200_batch_strides(int max_short, int max_long, long long* q_stride, long long* t_stride);
+SWB200_API int swb200_pack_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                                      const unsigned char* seq2_all, const long long* off2, const int* len2, long long npairs,
+                                      long long q_stride, long long t_stride, unsigned long long* q_words,
+                                      unsigned long long* t_words, int* q_len, int* t_len);
+SWB200_API int swb200_score_batch_packed(const unsigned long long* q_words, long long q_stride,
+                                         const unsigned long long* t_words, long long t_stride, const int* q_len,
+                                         const int* t_len, long long npairs, const swb200_params* p,
+                                         const swb200_options* opt, int* scores_out);
 
 /* Device-resident form: pack once (2-bit codes in HBM, the resident format), score many times.
  * All pointers are DEVICE pointers; max_short / max_long bound min(len1,len2) / max(len1,len2) over the

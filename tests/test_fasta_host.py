@@ -63,3 +63,16 @@ def test_plan_buckets_partition_and_order():
     # tiny classes are merged upward, never dropped
     few = fasta.plan_buckets(np.array([10, 500, 40]), np.array([20, 600, 50]), np.array([True] * 3), min_bucket=512)
     assert len(few) == 1 and few[0].kind == "batch" and few[0].cap == 1024 and sorted(few[0].index.tolist()) == [0, 1, 2]
+
+
+def test_pairs_beyond_the_batch_kernels_score_range_go_to_the_single_pair_engine():
+    """match * min(len) above the 16-bit batch limit (e.g. match 40 with 1 kb reads) must not reject the whole bucket:
+    plan_buckets routes such pairs to the single-pair engine."""
+    from concurrentproject_b200 import fasta
+    l1 = np.array([100, 900, 1000, 50]); l2 = np.array([1000, 1000, 1000, 60])
+    ok = np.ones(4, dtype=bool)
+    b = fasta.plan_buckets(l1, l2, ok, min_bucket=1, match=40)
+    single = [x for x in b if x.kind == "single"]
+    assert single and sorted(single[0].index.tolist()) == [1, 2]          # 40*900, 40*1000 > 32766-40; 40*100, 40*50 fit
+    assert all(i not in (1, 2) for x in b if x.kind == "batch" for i in x.index.tolist())
+    assert not [x for x in fasta.plan_buckets(l1, l2, ok, min_bucket=1, match=1) if x.kind == "single"]

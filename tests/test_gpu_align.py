@@ -66,8 +66,13 @@ def test_alignment_edge_cases():
     # one deleted stretch: a single gap, opened once
     a = rng.random_acgt(850, 0, 4000)
     b = np.concatenate([a[:2000], a[2007:]])
-    s, span, cigar = api.align(a, b)
-    assert s == 3993 - 7 and cigar == "2000=7I1993=" and span == (1, 1, 3993, 4000)
+    p = (2, -3, 5, 1)                                       # affine: one gap of 7 beats any split (with 1/-1/1/1 it only ties)
+    s, span, cigar = api.align(a, b, p)
+    m = re.fullmatch(r"(\d+)=7I(\d+)=", cigar)              # the gap may slide over equal neighbouring bases
+    assert s == 2 * 3993 - (5 + 6 * 1) and m and int(m.group(1)) + int(m.group(2)) == 3993 and span == (1, 1, 3993, 4000)
+    assert abs(int(m.group(1)) - 2000) <= 3
+    s, span, cigar = api.align(a, b)                        # linear gaps: same score as a single gap, whatever the split
+    assert s == 3993 - 7 and rescore(cigar, a, b, span, O.DEFAULT) == (s, True)
     # more than four distinct symbols: byte-compare kernels in all three passes (the reference compares raw bytes, main.cpp:28-33)
     x, y = b"HELLOWORLDGATTACAHELLO", b"XXWORLDGATTTACAYY"
     s, span, cigar = api.align(x, y)

@@ -88,3 +88,25 @@ def _pipelined_chunk_cases(api, fasta):
     a = [bytes(rng.random_acgt(23, k, 400 + k % 50)) for k in range(300)]
     b = [bytes(rng.mutate(x, 23, 1000 + k, 0.05, 0.01)) for k, x in enumerate(a)]
     assert np.array_equal(api.score_banded_batch(a, b, lo, hi), O.gotoh_banded_batch(a, b, lo, hi))
+
+
+def test_packed_host_batches():
+    """swb200_score_batch_packed: the host batch arrives in the resident 2-bit format (swb200_pack_batch_host, format
+    conversion only); ragged lengths, either sequence the shorter one, many small chunks through the copy/compute pipeline."""
+    from concurrentproject_b200 import api
+    s1, s2 = _ragged(41, 1200, 300, 1000)
+    s1[3], s2[3] = s2[3], s1[3]                                  # a pair whose FIRST sequence is the longer one
+    f1, o1, l1 = api._flatten(s1); f2, o2, l2 = api._flatten(s2)
+    qw, qs, tw, ts, ql, tl = api.pack_batch_host(f1, o1, l1, f2, o2, l2)
+    assert np.all(ql <= tl)
+    want = O.gotoh_batch(s1, s2)
+    assert np.array_equal(api.score_batch_packed(qw, qs, tw, ts, ql, tl), want)
+    assert np.array_equal(api.score_batch_packed(qw, qs, tw, ts, ql, tl, (2, -3, 5, 1)), O.gotoh_batch(s1, s2, (2, -3, 5, 1)))
+    api.configure("batch_chunk_bytes", "30000")
+    try:
+        assert np.array_equal(api.score_batch_packed(qw, qs, tw, ts, ql, tl), want)
+    finally:
+        api.configure("batch_chunk_bytes", "0")
+    with pytest.raises(api.SwbError):
+        api.pack_batch_host(np.frombuffer(b"ACGN", dtype=np.uint8), np.zeros(1, np.int64), np.array([4], np.int32),
+                            np.frombuffer(b"ACGT", dtype=np.uint8), np.zeros(1, np.int64), np.array([4], np.int32))
