@@ -41,6 +41,8 @@ EXPORTS = {
     "swb200_last_error": ([], C.c_char_p),
     "swb200_device_count": ([], C.c_int),
     "swb200_configure": ([C.c_char_p, C.c_char_p], C.c_int),
+    "swb200_plan": ([C.c_longlong, C.c_longlong, C.POINTER(Params), C.POINTER(Options), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                     C.POINTER(C.c_double)], C.c_int),
     "swb200_set_devices": ([C.c_int], C.c_int),
     "swb200_get_devices": ([], C.c_int),
     "swb200_score_banded": ([U8P, C.c_int, U8P, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_int)], C.c_int),

@@ -888,6 +888,22 @@ int swb200_configure(const char* key, const char* value) {
   return SWB200_OK;
 }
 
+// Diagnostic: what the planner would run for a pair (no GPU needed): out = {mode, rows, config, two_sided}, *est_cycles
+// = its cost estimate.  lanes: 16 packed, 17 packed re-based, 32; sms: SMs of ALL GPUs taking part.
+int swb200_plan(long long n, long long m, const swb200_params* pp, const swb200_options* oo, int lanes, int sms,
+                int allow_two_sided, int out[4], double* est_cycles) {
+  if (!out || n < 1 || m < 1 || sms < 1) return fail(SWB200_ERR_ARG, "bad plan arguments");
+  const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
+  const swb200_options o = oo ? *oo : swb200_options{};
+  const Plan pl = make_plan(n, m, p, o, lanes, sms, allow_two_sided != 0);
+  out[0] = pl.mode; out[1] = pl.R; out[2] = pl.config; out[3] = pl.two_sided ? 1 : 0;
+  if (est_cycles) {
+    const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
+    *est_cycles = estimate(LQ, LT, pl.mode, pl.R, pl.config, sms, pl.two_sided);
+  }
+  return SWB200_OK;
+}
+
 int swb200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

@@ -74,6 +74,12 @@ SWB200_API int swb200_device_count(void);
  *                                     with swb200_set_devices (default 2e11) */
 SWB200_API int swb200_configure(const char* key, const char* value);
 
+/* Diagnostic (needs no GPU): the kernel variant the planner picks for an n x m pair on `sms` SMs in all (148 per B200):
+ * out = {mode, rows, launch config, two_sided}, *est_cycles its cost estimate.  lanes: 16 = packed 16-bit, 17 = packed
+ * 16-bit re-based, 32 = 32-bit. */
+SWB200_API int swb200_plan(long long n, long long m, const swb200_params* p, const swb200_options* opt, int lanes, int sms,
+                           int allow_two_sided, int out[4], double* est_cycles);
+
 /* ---- several GPUs from one host process ------------------------------------------------------------
  * The reference's caller is a single-threaded C++ loop (TestFileWithGPU.cpp:57-94).  swb200_set_devices(G) makes
  * the HOST-buffer entry points below (and therefore the four legacy names) use devices 0 .. G-1:
