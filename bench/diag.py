@@ -87,7 +87,7 @@ if "cfgsweep" in what:
                         rec = {"kind": "cfgsweep", "n": nn, "mode": mode, "R": R, "config": config, "pure": pure, "ms": round(best, 4),
                                "bands": info["bands"], "warps": info["warps"], "rebased": info["rebased"], "ok": bool(pure or s == want)}
                         if pure:
-                            slack, hs = {1: (1, 0), 4: (1, 1)}.get(config, (0, 0))
+                            slack, hs = {1: (1, 0), 4: (1, 1), 5: (1, 0)}.get(config, (0, 0))
                             nsteps = (nn + 31 * (2 + slack + hs) + 1 + hs + 255) // 256 * 256
                             rounds = -(-info["bands"] // info["warps"])
                             rec["cyc_per_step"] = round(best * 1e-3 * MHZ * 1e6 / (nsteps * rounds), 2)

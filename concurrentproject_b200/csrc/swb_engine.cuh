@@ -79,9 +79,12 @@ struct EngineParams {
                                 //   nibble r = row r of the lane: bits 0-1 where H came from (0 diagonal, 1 E, 2 F), bit 2 E extended, bit 3 F extended
 };
 
+constexpr int kRawEntries = kChunk + 4;   // TMA flavour: 32 entries, one more when the first is odd, rounded to 16 bytes
 struct WarpSmem {
   uint32_t tab[2 * kTabRing];
   uint32_t inbox[4 * kInbox];   // plane 0: H-open (or packed H-open|F), plane 1: F (s32); each ring kept twice
+  alignas(16) uint2 raw[2][kRawEntries];   // TMA flavour: boundary entries as the bulk copy delivered them, double buffered
+  alignas(8) unsigned long long mbar[2];   // TMA flavour: one mbarrier per raw buffer
 };
 
 SWB_HD uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
@@ -222,7 +225,11 @@ constexpr int kBlock = kRebaseBlock;   // steps per block; nsteps of the 16-bit 
 //  cannot hide (measured: the step time did not move when every memory instruction and the shuffle were taken out).
 //  With HS 1 the hi sub-lane runs two T positions behind the lo sub-lane and consumes the lo bottom row of the step
 //  BEFORE the previous one: the recurrence spans two steps.  Costs one register and 31 more positions of lane skew.
-template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, int HS = 0>
+//  TMA (launch config 5): the next chunk's 32 boundary entries are fetched by ONE cp.async.bulk (272 bytes, global ->
+//  shared, completion on an mbarrier) issued by lane 0 half a chunk ahead, instead of 32 lanes' speculative loads; at
+//  the chunk start the warp waits on the mbarrier and every lane takes its {value, tag} from shared memory.  Tag
+//  validation, the out-of-line poll and everything after it are unchanged.  Device only (the emulator runs TMA = false).
+template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, int HS = 0, bool TMA = false>
 SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
   static_assert(SLACK == 0 || SLACK == 1, "a shuffled boundary value is consumed in the same step or one step later");
   static_assert(HS == 0 || HS == 1, "the hi sub-lane trails the lo sub-lane by one or two positions");
@@ -244,6 +251,14 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   int base = 0, best_abs = 0;          // RB only
   uint32_t floorw = 0;                 // RB only: packed max(-base, -30000)
   Waiter wt{P.spin_limit, false};
+#if SWB_DEVICE_CODE
+  uint32_t tma_phase0 = 0, tma_phase1 = 0;      // parity of the next completion of mbar[0] / mbar[1]
+  if (TMA) {
+    if (lane == 0) { mbar_init(&sm->mbar[0], 1); mbar_init(&sm->mbar[1], 1); }
+    mbar_init_fence();
+    w.sync();
+  }
+#endif
   // P is picked at run time between the two halves of a launch, so every P.field inside a loop is a constant load
   // through a register index; the one the chunk loop needs is kept in a register.
   // (measured: +4.8 % on cfg2 with one warp per scheduler, -2.5 % with two warps per scheduler: only the former do it)
@@ -320,6 +335,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
     uint64_t twpref = (kChunk + lane < LT) ? ld_early_u64(SWB_T_PACKED + ((kChunk + lane) >> 5)) : 0ull;
     uint2 epref = make_uint2(0u, 0u), bpref = make_uint2(0u, 0u);
     bool live = !zero_src;             // warp-uniform: top boundary entries are expected (false: zero border, or after a timeout)
+    bool tma_inflight = false;         // TMA flavour: a bulk copy for the next chunk has been issued
     if (live && SLACK + lane < LT) {
       const long long j = in_base + SLACK + lane + SKEW;
       epref = ld_entry(in + (j & in_mask));
@@ -410,6 +426,18 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         const int q = i0 + SLACK + lane;
         const long long j = in_base + q + SKEW;                           // producer step that emitted q
         const bool need = live && q < LT;
+#if SWB_DEVICE_CODE
+        if (TMA && tma_inflight) {                                        // warp-uniform
+          const int b = (i0 / kChunk) & 1;
+          unsigned long long* bar = &sm->mbar[b];
+          const uint32_t ph = b ? tma_phase1 : tma_phase0;
+          while (!mbar_try_wait(bar, ph)) {}
+          if (b) tma_phase1 ^= 1u; else tma_phase0 ^= 1u;
+          const uint32_t s0 = (uint32_t)((in_base + i0 + SLACK + SKEW) & in_mask);
+          epref = sm->raw[b][lane + (s0 & 1u)];
+          tma_inflight = false;
+        }
+#endif
         {
           const uint32_t want = in_tag | ((uint32_t)(j >> in_shift) & 0xFFu);
           const long long bj = j >> 8;
@@ -536,6 +564,25 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
 #pragma unroll (kU)
         for (int k = 0; k < kChunk / 2; ++k) step(k);
+#if SWB_DEVICE_CODE
+        if (TMA) {
+          // one bulk copy for the whole next chunk: entries a0 .. a0+33 of the ring (a0 even: 16-byte aligned), split in
+          // two when the 34 entries run over the end of the ring (ring lengths are even, so both parts stay 16-byte multiples)
+          if (live && i0 + kChunk + SLACK < LT) {                         // warp-uniform: lane 0's next entry exists
+            const int b = ((i0 / kChunk) + 1) & 1;
+            if (lane == 0) {
+              const uint32_t s0 = (uint32_t)((in_base + i0 + kChunk + SLACK + SKEW) & in_mask);
+              const uint32_t a0 = s0 & ~1u;
+              const uint32_t ring_len = in_mask + 1u;
+              const uint32_t n1 = (a0 + (kChunk + 2) <= ring_len) ? (uint32_t)(kChunk + 2) : ring_len - a0;
+              mbar_expect_tx(&sm->mbar[b], (kChunk + 2) * 8u);
+              bulk_g2s(&sm->raw[b][0], in + a0, n1 * 8u, &sm->mbar[b]);
+              if (n1 < (uint32_t)(kChunk + 2)) bulk_g2s(&sm->raw[b][n1], in, ((kChunk + 2) - n1) * 8u, &sm->mbar[b]);
+            }
+            tma_inflight = true;
+          }
+        } else
+#endif
         if (spec) epref = ld_entry(spec_e);
         if (RB && spec) bpref = ld_entry(spec_b);
 #pragma unroll (kU)

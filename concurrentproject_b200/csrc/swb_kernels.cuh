@@ -10,9 +10,11 @@ namespace swb {
 //           the independent E / substitution work once R is large enough)
 // config 4: config 1 plus the same slack for the hand-off inside a thread (HS 1: the hi sub-lane runs two positions
 //           behind the lo sub-lane, which takes the row chain out of the per-step recurrence); packed 16-bit modes only
-constexpr int kNumConfigs = 4;
+// config 5: config 1 with the boundary chunk fetched by one cp.async.bulk + mbarrier (TMA) instead of 32 lanes' loads;
+//           packed 16-bit modes only
+constexpr int kNumConfigs = 5;
 SWB_HD int config_wpc(int config) { return config == 2 ? 8 : 4; }
-SWB_HD int config_slack(int config) { return (config == 1 || config == 4) ? 1 : 0; }
+SWB_HD int config_slack(int config) { return (config == 1 || config == 4 || config == 5) ? 1 : 0; }
 SWB_HD int config_hs(int config) { return config == 4 ? 1 : 0; }
 // steps by which the last sub-lane of a band trails the first (what a band adds to the sweep; entry slot - T position)
 SWB_HD int config_skew(int config, int mode) {
@@ -46,7 +48,7 @@ struct EngineLaunch {
 };
 
 #ifdef __CUDACC__
-template <int R, int MODE, int SLACK, int WPC, int HS = 0>
+template <int R, int MODE, int SLACK, int WPC, int HS = 0, bool TMA = false>
 __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineLaunch L) {
   __shared__ WarpSmem sm[WPC];
   WarpCtx w{(int)(threadIdx.x & 31)};
@@ -68,8 +70,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
   else if constexpr (MODE == 9) engine_warp_s32<R, SLACK, true, SHORT, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 10) engine_warp_s32<R, SLACK, false, false, false, true, true>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 11) engine_warp_s32<R, SLACK, true, false, false, true, true>(P, w, lw, &sm[wi]);
-  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT, HS>(P, w, lw, &sm[wi]);
-  else engine_warp_s16<R, MODE, SLACK, false, SHORT, HS>(P, w, lw, &sm[wi]);
+  else if constexpr (MODE >= 3) engine_warp_s16<R, MODE - 3, SLACK, true, SHORT, HS, TMA>(P, w, lw, &sm[wi]);
+  else engine_warp_s16<R, MODE, SLACK, false, SHORT, HS, TMA>(P, w, lw, &sm[wi]);
 }
 
 template <int MODE>
@@ -78,7 +80,10 @@ static const void* engine_kernel_lookup(int R, int config) {
   if (config < 1 || config > kNumConfigs || (config > 3 && !S16)) return nullptr;
 #define SWB_CASE(RR)                                                             \
   case RR:                                                                       \
-    if constexpr (S16) { if (config == 4) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 1>; }   \
+    if constexpr (S16) {                                                         \
+      if (config == 4) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 1>;  \
+      if (config == 5) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 0, true>;  \
+    }                                                                            \
     return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
          : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \
                        : (const void*)sw_engine_kernel<RR, MODE, 0, 4>;

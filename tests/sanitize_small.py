@@ -27,7 +27,7 @@ checks = 0
 a, b = planted(1, 1500)
 want = O.gotoh_rolling(a, b)
 for kw in (dict(), dict(no_linear=True), dict(lanes=32), dict(config=2, rows=2), dict(config=3, rows=2, no_linear=True),
-           dict(config=4, rows=2), dict(config=4, rows=3, no_linear=True), dict(rebase=1, rows=2), dict(rebase=1, no_linear=True, config=2, rows=2),
+           dict(config=4, rows=2), dict(config=4, rows=3, no_linear=True), dict(config=5, rows=2), dict(config=5, rows=1, no_linear=True, rebase=1), dict(rebase=1, rows=2), dict(rebase=1, no_linear=True, config=2, rows=2),
            dict(two_sided=1, rows=1), dict(two_sided=1, rows=1, no_linear=True, rebase=1), dict(two_sided=-1, rows=1, ctas=2)):
     got = api.score(a, b, **kw)
     assert got == want, (kw, got, want)

@@ -69,9 +69,11 @@ def test_reference_fixture_scores_other_params(api):
         assert api.score(a, b, p, lanes=32) == c["score_main"], c
 
 
-@pytest.mark.parametrize("config", [1, 2, 3])
+@pytest.mark.parametrize("config", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("lanes,no_linear", [(16, False), (16, True), (32, True)])
 def test_every_kernel_variant_against_oracle(api, config, lanes, no_linear):
+    if config > 3 and lanes == 32:
+        pytest.skip("launch configs 4 (slack inside a thread) and 5 (TMA-staged boundary chunk) exist for packed 16-bit lanes")
     a, b = planted(500, 3000)
     c, d = rng.random_acgt(501, 0, 2100), rng.random_acgt(501, 1, 5000)
     # (3,-2,2,2), (3,-2,3,1): positive drift, every cell matters; (2,-1,1,3): opening a gap is cheaper than extending it
@@ -314,7 +316,7 @@ def test_banded_other_bands_params_and_edges(api):
         api.score_banded_batch(e1, e2, -10, 10)      # only 64-diagonal bands in this kernel
 
 
-@pytest.mark.parametrize("config", [1, 2, 3])
+@pytest.mark.parametrize("config", [1, 2, 3, 4, 5])
 def test_rebased_16_bit_lanes(api, config):
     """Scores far beyond 32767 in packed 16-bit lanes relative to a moving base: the level climbs (identical
     prefix), falls back to ~0 (unrelated middle), climbs again; every re-base direction is exercised."""
