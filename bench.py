@@ -439,7 +439,7 @@ def batch_record(env, args, name, steps, warmup):
 
     def run_kernel():
         if banded:
-            batch.score_banded(scores.data_ptr(), lo, hi, stream=stream.cuda_stream, no_linear=args.no_linear)
+            batch.score_banded(scores.data_ptr(), lo, hi, stream=stream.cuda_stream, no_linear=args.no_linear, config=args.banded_config)
         else:
             batch.score(scores.data_ptr(), stream=stream.cuda_stream, no_linear=args.no_linear)
 
@@ -597,6 +597,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=ALL_WORKLOADS)
     ap.add_argument("--no-extra", action="store_true", help="headline only: skip the cfg3 ring and cfg4 batch sub-records")
     ap.add_argument("--lanes32", action="store_true", help="ring workloads: force the 32-bit kernel")
+    ap.add_argument("--banded-config", type=int, default=0, help="banded workloads: 16 = the 16-threads-per-pair kernel layout")
     ap.add_argument("--one-sided", action="store_true", help="ring workloads: never sweep from both ends")
     ap.add_argument("--no-linear", action="store_true",
                     help="keep the general affine kernel although GAP_INIT == GAP_EXT (default: use the exact E/F-free kernel)")

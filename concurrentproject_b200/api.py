@@ -217,14 +217,14 @@ def score_batch_flat(flat1: np.ndarray, off1: np.ndarray, len1: np.ndarray, flat
 
 
 def score_banded_batch(seqs1, seqs2, band_lo: int = -32, band_hi: int = 31, params: Sequence[int] = DEFAULT_PARAMS, *,
-                       no_linear: bool = False) -> np.ndarray:
+                       no_linear: bool = False, config: int = 0) -> np.ndarray:
     """Banded scores of many HOST pairs: cell (i, j) counts iff band_lo <= j - i <= band_hi (64 diagonals)."""
     if len(seqs1) != len(seqs2):
         raise ValueError("seqs1 and seqs2 differ in length")
     f1, o1, l1 = _flatten(seqs1)
     f2, o2, l2 = _flatten(seqs2)
     out = np.zeros(len(seqs1), dtype=np.int32)
-    p, o = _params(params), _options(no_linear=no_linear)
+    p, o = _params(params), _options(no_linear=no_linear, config=config)      # config 16: the 16-threads-per-pair layout
     LL, I = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
     rc = _lib.load().swb200_score_banded_batch(_ptr(f1), o1.ctypes.data_as(LL), l1.ctypes.data_as(I), _ptr(f2),
                                                o2.ctypes.data_as(LL), l2.ctypes.data_as(I), len(seqs1), band_lo, band_hi,
@@ -270,8 +270,8 @@ class PackedBatch:
             raise SwbError(rc, "swb200_batch_score")
 
     def score_banded(self, d_scores: int, band_lo: int, band_hi: int, params: Sequence[int] = DEFAULT_PARAMS, *, stream: int = 0,
-                     no_linear: bool = False) -> None:
-        p, o = _params(params), _options(no_linear=no_linear)
+                     no_linear: bool = False, config: int = 0) -> None:
+        p, o = _params(params), _options(no_linear=no_linear, config=config)
         rc = _lib.load().swb200_batch_score_banded(self.handle, band_lo, band_hi, C.byref(p), C.byref(o), C.c_void_p(stream),
                                                    C.c_void_p(d_scores))
         if rc != 0:

@@ -1330,23 +1330,25 @@ static int launch_banded_score(swb200_ctx* c, const BatchView& v, int band_lo, c
                                const swb200_options& o, cudaStream_t s, int* d_scores, swb200_run_info* info) {
   if (v.npairs == 0) return SWB200_OK;
   const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
-  const void* kern = swb::banded_kernel(mode);
-  // 4 CTAs of 35 KB static shared memory per SM: ask for the large shared-memory carve-out (latency hiding: the step
-  // loop is a chain of SHFL -> DPX -> SHFL, ncu shows short-scoreboard stalls on top)
+  // two layouts: 8 threads per pair with four register sets each (round 2: half the shuffles per cell; the default) and
+  // 16 threads per pair with two (options.config = 16, kept for comparison)
+  const bool wide = o.config == 16;
+  const void* kern = wide ? swb::banded_kernel(mode) : swb::banded8_kernel(mode);
+  const int threads = wide ? 256 : 128, pairs_per_cta = wide ? 16 : 16;
+  // several CTAs of 34-35 KB static shared memory per SM: ask for the large shared-memory carve-out
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   swb::BandedParams P{};
   P.a_words = v.q_words; P.b_words = v.t_words; P.a_len = v.q_len; P.b_len = v.t_len;
   P.a_stride = v.q_stride; P.b_stride = v.t_stride; P.npairs = v.npairs; P.band_lo = band_lo; P.scores = d_scores;
   P.match = p.match; P.mismatch = p.mismatch; P.gap_init = p.gap_init; P.gap_ext = p.gap_ext;
   int per_sm = 0;
-  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
   per_sm = std::max(per_sm, 1);
-  const long long groups = (v.npairs + 1) / 2;
-  const long long ctas = std::max<long long>(1, std::min<long long>((groups + 7) / 8, (long long)c->sms * per_sm));
+  const long long ctas = std::max<long long>(1, std::min<long long>((v.npairs + pairs_per_cta - 1) / pairs_per_cta, (long long)c->sms * per_sm));
   void* args[] = {&P};
-  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3(256), args, 0, s));
-  info->lanes = 16; info->linear = mode == 1; info->rows = 0; info->config = 200; info->ctas = (int)ctas;
-  info->warps = (int)ctas * 8; info->bands = swb::kBandWidth; info->engine_launches += 1;
+  SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3((unsigned)threads), args, 0, s));
+  info->lanes = 16; info->linear = mode == 1; info->rows = 0; info->config = wide ? 216 : 208; info->ctas = (int)ctas;
+  info->warps = (int)ctas * (threads / 32); info->bands = swb::kBandWidth; info->engine_launches += 1;
   return SWB200_OK;
 }
 

@@ -39,6 +39,12 @@ static void run_banded_lane(const BandedParams* P, WarpShared* ws, int lane, lon
   banded_warp<MODE>(*P, w, wid, nw, sm);
 }
 
+template <int MODE>
+static void run_banded8_lane(const BandedParams* P, WarpShared* ws, int lane, long long wid, long long nw, BandedWarpSmem8* sm) {
+  WarpCtx w{lane, ws};
+  banded_warp8<MODE>(*P, w, wid, nw, sm);
+}
+
 int main(int argc, char** argv) {
   if (argc < 6) { fprintf(stderr, "usage: batch_emu pairs.bin batch|banded R MODE G [ma mi gi ge [band_lo]]\n"); return 2; }
   FILE* f = fopen(argv[1], "rb");
@@ -82,10 +88,17 @@ int main(int argc, char** argv) {
     BandedParams P{};
     P.a_words = qw.data(); P.b_words = tw.data(); P.a_len = ql.data(); P.b_len = tl.data(); P.a_stride = qs; P.b_stride = ts;
     P.npairs = np; P.band_lo = band_lo; P.scores = scores.data(); P.match = ma; P.mismatch = mi; P.gap_init = gi; P.gap_ext = ge;
-    std::vector<BandedWarpSmem> sm(W);
-    auto fn = mode ? run_banded_lane<1> : run_banded_lane<0>;
-    for (int w = 0; w < W; ++w) for (int l = 0; l < 32; ++l) th.emplace_back(fn, &P, &ws[w], l, (long long)w, (long long)W, &sm[w]);
-    for (auto& x : th) x.join();
+    if (G == 16) {                                     // the 16-threads-per-pair layout
+      std::vector<BandedWarpSmem> sm(W);
+      auto fn = mode ? run_banded_lane<1> : run_banded_lane<0>;
+      for (int w = 0; w < W; ++w) for (int l = 0; l < 32; ++l) th.emplace_back(fn, &P, &ws[w], l, (long long)w, (long long)W, &sm[w]);
+      for (auto& x : th) x.join();
+    } else {                                           // G = 8: eight threads per pair, four register sets each
+      std::vector<BandedWarpSmem8> sm(W);
+      auto fn = mode ? run_banded8_lane<1> : run_banded8_lane<0>;
+      for (int w = 0; w < W; ++w) for (int l = 0; l < 32; ++l) th.emplace_back(fn, &P, &ws[w], l, (long long)w, (long long)W, &sm[w]);
+      for (auto& x : th) x.join();
+    }
   }
   printf("scores");
   for (int k = 0; k < np; ++k) printf(" %d", scores[k]);

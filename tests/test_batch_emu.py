@@ -59,7 +59,9 @@ def test_batch_kernel_body(emu, R, G, max_read):
         assert emu(s1, s2, "batch", R, mode, G, p) == O.gotoh_batch(s1, s2, p).tolist(), (R, G, p, mode)
 
 
-def test_banded_kernel_body(emu):
+@pytest.mark.parametrize("G", [16, 8])
+def test_banded_kernel_body(emu, G):
+    """Both layouts of the banded kernel: 16 threads per pair with two register sets, 8 threads with four."""
     r = np.random.default_rng(9)
     a = [bytes(rng.random_acgt(60, k, int(r.integers(1, 420)))) for k in range(7)]
     b = [bytes(rng.mutate(np.frombuffer(x, np.uint8), 60, 100 + k, 0.08, 0.03)) if k % 3 else bytes(rng.random_acgt(61, k, 300))
@@ -67,4 +69,4 @@ def test_banded_kernel_body(emu):
     for lo in (-32, -5, 0, -60, 17):
         for p, mode in ((O.DEFAULT, 1), (O.DEFAULT, 0), ((2, -3, 5, 1), 0), ((3, -2, 3, 1), 0), ((3, -2, 2, 2), 1)):
             want = O.gotoh_banded_batch(a, b, lo, lo + 63, p).tolist()
-            assert emu(a, b, "banded", 0, mode, 8, p, band_lo=lo) == want, (lo, p, mode)
+            assert emu(a, b, "banded", 0, mode, G, p, band_lo=lo) == want, (lo, p, mode, G)

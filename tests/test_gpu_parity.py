@@ -292,11 +292,12 @@ def _long_read_pairs(seed, npairs, n):
     return s1, s2
 
 
+@pytest.mark.parametrize("config", [0, 16])
 @pytest.mark.parametrize("no_linear", [False, True])
-def test_banded_batch_against_oracle(api, no_linear):
+def test_banded_batch_against_oracle(api, no_linear, config):
     s1, s2 = _long_read_pairs(800, 24, 3000)
     want = O.gotoh_banded_batch(s1, s2, -32, 31)
-    got = api.score_banded_batch(s1, s2, -32, 31, no_linear=no_linear)
+    got = api.score_banded_batch(s1, s2, -32, 31, no_linear=no_linear, config=config)
     assert got.tolist() == want.tolist()
     assert want.max() > 500           # the planted similarity really is found inside the band
     full = O.gotoh_batch(s1, s2)
