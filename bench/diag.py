@@ -76,7 +76,7 @@ if "cfgsweep" in what:
                         try:
                             for _ in range(3 if nn == 100000 else 2):
                                 s = ctx.score_device(x.data_ptr(), nn, y.data_ptr(), nn, rows=R, config=config, no_linear=no_lin,
-                                                     two_sided=(-1 if pure else 1))
+                                                     two_sided=(-1 if pure else 1), rebase=int(os.environ.get("DIAG_REBASE", "0")))
                                 info = ctx.last_run()
                                 best = info["engine_ms"] if best is None else min(best, info["engine_ms"])
                         except Exception as e:

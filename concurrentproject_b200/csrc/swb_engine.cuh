@@ -23,6 +23,7 @@
 // gap_ext the E/F registers are provably redundant (E = H_left-g, F = H_up-g) and MODE 1 drops them.
 #pragma once
 #include "swb_device.cuh"
+#include <type_traits>
 
 namespace swb {
 
@@ -393,6 +394,10 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         if (emit) st_entry(out_bases + (((out_base + i8) >> 8) & outb_mask), (uint32_t)base,
                            out_tag | ((uint32_t)(((out_base + i8) >> 8) >> out_shift) & 0xFFu));
       }
+      // Re-based lanes far above zero: the clamp at the zero floor cannot bind (floorw is then the stand-in -30000, and
+      // every live value is within +-20000 of the base or the range check above fires and the host repeats in 32 bit),
+      // so this block's steps run without it.  Every band starts at base 0, i.e. with the clamp.
+      const bool nofloor = RB && base > 30000 && !(P.dbg & 4);
       // every boundary entry of the steps before this block has been read: tell the producer (ring back-pressure)
       if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + i8 + SLACK));
       // (c) ring back-pressure: never overwrite an entry the consumer has not read yet
@@ -474,7 +479,10 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         const uint32_t otag = out_tag | ((uint32_t)((out_base + i0) >> out_shift) & 0xFFu);
 
         uint32_t xnext = inbp[0];                        // loaded one step ahead of use (like Tnext)
-        auto step = [&](const int k) {
+        // FLOORC: std::true_type = clamp at the zero floor (-base in re-based lanes), std::false_type = re-based lanes
+        // whose base is so high that the floor cannot bind (see `nofloor` above): one instruction less per row
+        auto step = [&](const int k, auto FLOORC) {
+          constexpr bool FL = decltype(FLOORC)::value;
           const uint32_t Tlo = Tnext;
           const uint32_t xin = xnext;
           Tnext = tabp[k + 1];
@@ -514,12 +522,12 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
               uint32_t h;
               if (MODE == 0) {
                 E[r] = addmax16x2(E[r], next, old);
-                const uint32_t m = RB ? max16x2(addmax16x2(diag, s, E[r]), floorw) : addmaxrelu16x2(diag, s, E[r]);
+                const uint32_t m = RB ? (FL ? max16x2(addmax16x2(diag, s, E[r]), floorw) : addmax16x2(diag, s, E[r])) : addmaxrelu16x2(diag, s, E[r]);
                 F = addmax16x2(F, r == 0 ? next : fnext, X);
                 X = add16x2(m, nopen);
                 h = max16x2(m, F);
               } else if (RB) {
-                const uint32_t t = max3_16x2(add16x2(diag, s), old, floorw);
+                const uint32_t t = FL ? max3_16x2(add16x2(diag, s), old, floorw) : addmax16x2(diag, s, old);
                 h = r == 0 ? max16x2(t, X) : addmax16x2(hprev, nopen, t);
               } else {
                 const uint32_t t = addmax16x2(diag, s, old);
@@ -542,10 +550,10 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
               if (MODE == 0) {
                 E[r] = addmax16x2(E[r], next, old);
                 F = addmax16x2(F, next, Hup);
-                h = RB ? max16x2(max3_16x2(d, E[r], F), floorw) : max3relu16x2(d, E[r], F);
+                h = RB ? (FL ? max16x2(max3_16x2(d, E[r], F), floorw) : max3_16x2(d, E[r], F)) : max3relu16x2(d, E[r], F);
               } else {
                 // non-RB: the clamp at 0 rides on the fused add-max, the second max is the plain full-rate VIMNMX
-                h = RB ? max16x2(max3_16x2(d, old, Hup), floorw) : max16x2(addmaxrelu16x2(diag, s, old), Hup);
+                h = RB ? (FL ? max16x2(max3_16x2(d, old, Hup), floorw) : max16x2(addmax16x2(diag, s, old), Hup)) : max16x2(addmaxrelu16x2(diag, s, old), Hup);
               }
               Ho[r] = add16x2(h, nopen);
               Hup = Ho[r];
@@ -562,8 +570,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         // Two sequential half-chunk loops (not a nested one: that cost more in code generation than it saved) with
         // the speculative boundary loads of the next chunk in between: the band above only has to be
         // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
-#pragma unroll (kU)
-        for (int k = 0; k < kChunk / 2; ++k) step(k);
+        auto mid_chunk = [&]() {
 #if SWB_DEVICE_CODE
         if (TMA) {
           // one bulk copy for the whole next chunk: entries a0 .. a0+33 of the ring (a0 even: 16-byte aligned), split in
@@ -585,8 +592,20 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
 #endif
         if (spec) epref = ld_entry(spec_e);
         if (RB && spec) bpref = ld_entry(spec_b);
+        };
+        if (RB && nofloor) {                  // warp-uniform, constant over a block of 256 steps
 #pragma unroll (kU)
-        for (int k = kChunk / 2; k < kChunk; ++k) step(k);
+          for (int k = 0; k < kChunk / 2; ++k) step(k, std::false_type{});
+          mid_chunk();
+#pragma unroll (kU)
+          for (int k = kChunk / 2; k < kChunk; ++k) step(k, std::false_type{});
+        } else {
+#pragma unroll (kU)
+          for (int k = 0; k < kChunk / 2; ++k) step(k, std::true_type{});
+          mid_chunk();
+#pragma unroll (kU)
+          for (int k = kChunk / 2; k < kChunk; ++k) step(k, std::true_type{});
+        }
 #if defined(SWB_ENABLE_PROF) && SWB_DEVICE_CODE
         { const long long tp2 = clock64(); prof_pro += tp1 - tp0; prof_steps += tp2 - tp1; prof_polls += bud0 - wt.budget; prof_chunks += 1; }
 #endif

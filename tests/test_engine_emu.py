@@ -210,3 +210,16 @@ def test_slack_inside_a_thread(emu, mode, slack):
         a = rng.random_acgt(3277, 0, 2500)
         b = rng.mutate(a, 3277, 1, 0.05, 0.02)
         assert emu(a, b, 1, mode, slack, 3, 1, p, hs=True) == (O.gotoh_rolling(a, b, p), 0)
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+def test_rebased_lanes_far_above_zero_run_without_the_floor(emu, mode):
+    """Score ~47 000 (match 10): once a band's base passes 30 000 its 256-step blocks run the step loop WITHOUT the clamp
+    at the zero floor (swb_engine.cuh: nofloor) -- every band still starts with it, at base 0."""
+    p = (10, -8, 10, 5) if mode == 3 else (10, -8, 7, 7)
+    a = rng.random_acgt(4242, 0, 5200)
+    b = rng.mutate(a, 4242, 1, 0.04, 0.02)
+    want = O.gotoh_rolling(a, b, p)
+    assert want > 40000
+    assert emu(a, b, 4, mode, 0, 2, 2, p) == (want, 0)
+    assert emu(a, b, 2, mode, 1, 2, 1, p, hs=True) == (want, 0)
