@@ -397,7 +397,8 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       // Re-based lanes far above zero: the clamp at the zero floor cannot bind (floorw is then the stand-in -30000, and
       // every live value is within +-20000 of the base or the range check above fires and the host repeats in 32 bit),
       // so this block's steps run without it.  Every band starts at base 0, i.e. with the clamp.
-      const bool nofloor = RB && base > 30000 && !(P.dbg & 4);
+      // (linear-gap kernels only: measured -3.6 % on cfg3; the affine kernel got 3 % SLOWER with a second copy of its larger loop)
+      const bool nofloor = RB && MODE == 1 && base > 30000 && !(P.dbg & 4);
       // every boundary entry of the steps before this block has been read: tell the producer (ring back-pressure)
       if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + i8 + SLACK));
       // (c) ring back-pressure: never overwrite an entry the consumer has not read yet
