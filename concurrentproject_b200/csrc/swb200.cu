@@ -448,6 +448,9 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
   return (start + (double)(LT + skew)) * cyc_step;
 }
 
+struct Plan;
+const void* kernel_for(const Plan& pl);
+
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms,
                bool allow_two_sided = false) {
   Plan pl{};
@@ -470,7 +473,8 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
   double best = 1e300;
   for (int ci = 1; ci <= swb::kNumConfigs; ++ci) {
     if (o.config && o.config != ci) continue;
-    if (ci > 3 && (swb::mode_is_s32(pl.mode) || !o.config)) continue;      // config 4: 16-bit lanes, and (until fitted) only on request
+    if (ci > 3 && (swb::mode_is_s32(pl.mode) || !o.config)) continue;      // configs 4-6: 16-bit lanes, and only on request
+    { Plan probe = pl; probe.R = 1; probe.config = ci; if (!kernel_for(probe)) continue; }
     for (int ri = 0; ri < swb::kNumRowChoices; ++ri) {
       const int R = swb::kRowChoices[ri];
       if (o.rows && o.rows != R) continue;

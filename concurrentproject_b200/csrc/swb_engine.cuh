@@ -84,8 +84,10 @@ constexpr int kRawEntries = kChunk + 4;   // TMA flavour: 32 entries, one more w
 struct WarpSmem {
   uint32_t tab[2 * kTabRing];
   uint32_t inbox[4 * kInbox];   // plane 0: H-open (or packed H-open|F), plane 1: F (s32); each ring kept twice
-  alignas(16) uint2 raw[2][kRawEntries];   // TMA flavour: boundary entries as the bulk copy delivered them, double buffered
-  alignas(8) unsigned long long mbar[2];   // TMA flavour: one mbarrier per raw buffer
+};
+struct WarpSmemTma : WarpSmem {            // launch config 5 only
+  alignas(16) uint2 raw[2][kRawEntries];   // boundary entries as the bulk copy delivered them, double buffered
+  alignas(8) unsigned long long mbar[2];   // one mbarrier per raw buffer
 };
 
 SWB_HD uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
@@ -231,7 +233,9 @@ constexpr int kBlock = kRebaseBlock;   // steps per block; nsteps of the 16-bit 
 //  the chunk start the warp waits on the mbarrier and every lane takes its {value, tag} from shared memory.  Tag
 //  validation, the out-of-line poll and everything after it are unchanged.  Device only (the emulator runs TMA = false).
 template <int R, int MODE, int SLACK, bool RB = false, bool SHORT = true, int HS = 0, bool TMA = false>
-SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm) {
+SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, WarpSmem* sm_base) {
+  typedef typename std::conditional<TMA, WarpSmemTma, WarpSmem>::type Smem;
+  Smem* sm = static_cast<Smem*>(sm_base);
   static_assert(SLACK == 0 || SLACK == 1, "a shuffled boundary value is consumed in the same step or one step later");
   static_assert(HS == 0 || HS == 1, "the hi sub-lane trails the lo sub-lane by one or two positions");
   constexpr int SK = 2 + SLACK + HS;   // T positions between neighbouring lanes
@@ -254,7 +258,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
   Waiter wt{P.spin_limit, false};
 #if SWB_DEVICE_CODE
   uint32_t tma_phase0 = 0, tma_phase1 = 0;      // parity of the next completion of mbar[0] / mbar[1]
-  if (TMA) {
+  if constexpr (TMA) {
     if (lane == 0) { mbar_init(&sm->mbar[0], 1); mbar_init(&sm->mbar[1], 1); }
     mbar_init_fence();
     w.sync();
@@ -384,7 +388,12 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
             const uint32_t dw = pack2(-delta);
 #pragma unroll
             for (int r = 0; r < R; ++r) { Ho[r] = add16x2(Ho[r], dw); E[r] = add16x2(E[r], dw); }
-            Fbot = add16x2(Fbot, dw); up_prev = add16x2(up_prev, dw); xsend = add16x2(xsend, dw); yold = add16x2(yold, dw);
+            // up_prev / yold may hold the stand-in for a boundary value that does not exist (T positions beyond LT,
+            // -30000 - open once the base is high): clamp before shifting, or a rising base wraps it around to a huge
+            // positive value (seen on a 4 M x 4 M pair whose LT is a multiple of the block: score 483 137 for 456 586)
+            const uint32_t lowc = pack2(delta > 2768 ? -30000 + delta : -32768);
+            Fbot = add16x2(Fbot, dw); xsend = add16x2(xsend, dw);
+            up_prev = add16x2(max16x2(up_prev, lowc), dw); yold = add16x2(max16x2(yold, lowc), dw);
             if (HS) { HoLast_d = add16x2(HoLast_d, dw); Fbot_d = add16x2(Fbot_d, dw); }
             base += delta;
             floorw = pack2(-base > -30000 ? -base : -30000);
@@ -433,7 +442,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         const long long j = in_base + q + SKEW;                           // producer step that emitted q
         const bool need = live && q < LT;
 #if SWB_DEVICE_CODE
-        if (TMA && tma_inflight) {                                        // warp-uniform
+        if constexpr (TMA) if (tma_inflight) {                            // warp-uniform
           const int b = (i0 / kChunk) & 1;
           unsigned long long* bar = &sm->mbar[b];
           const uint32_t ph = b ? tma_phase1 : tma_phase0;
@@ -573,7 +582,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         // SKEW + 1.5 chunks ahead instead of SKEW + 2 chunks.
         auto mid_chunk = [&]() {
 #if SWB_DEVICE_CODE
-        if (TMA) {
+        if constexpr (TMA) {
           // one bulk copy for the whole next chunk: entries a0 .. a0+33 of the ring (a0 even: 16-byte aligned), split in
           // two when the 34 entries run over the end of the ring (ring lengths are even, so both parts stay 16-byte multiples)
           if (live && i0 + kChunk + SLACK < LT) {                         // warp-uniform: lane 0's next entry exists

@@ -12,9 +12,12 @@ namespace swb {
 //           behind the lo sub-lane, which takes the row chain out of the per-step recurrence); packed 16-bit modes only
 // config 5: config 1 with the boundary chunk fetched by one cp.async.bulk + mbarrier (TMA) instead of 32 lanes' loads;
 //           packed 16-bit modes only
-constexpr int kNumConfigs = 5;
-SWB_HD int config_wpc(int config) { return config == 2 ? 8 : 4; }
-SWB_HD int config_slack(int config) { return (config == 1 || config == 4 || config == 5) ? 1 : 0; }
+// config 6: 12 warps per CTA (three per scheduler), slack step, short-chain row loop, at most 10 rows per
+//           sub-lane (170 registers per thread, 36 KB of shared memory): for pairs with far more bands than warps, where
+//           the schedulers and not the pipeline depth are the limit; packed 16-bit modes only
+constexpr int kNumConfigs = 6;
+SWB_HD int config_wpc(int config) { return config == 2 ? 8 : (config == 6 ? 12 : 4); }
+SWB_HD int config_slack(int config) { return (config == 1 || config == 4 || config == 5 || config == 6) ? 1 : 0; }
 SWB_HD int config_hs(int config) { return config == 4 ? 1 : 0; }
 // steps by which the last sub-lane of a band trails the first (what a band adds to the sweep; entry slot - T position)
 SWB_HD int config_skew(int config, int mode) {
@@ -50,7 +53,7 @@ struct EngineLaunch {
 #ifdef __CUDACC__
 template <int R, int MODE, int SLACK, int WPC, int HS = 0, bool TMA = false>
 __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_constant__ EngineLaunch L) {
-  __shared__ WarpSmem sm[WPC];
+  __shared__ typename std::conditional<TMA, WarpSmemTma, WarpSmem>::type sm[WPC];
   WarpCtx w{(int)(threadIdx.x & 31)};
   const int wi = (int)(threadIdx.x >> 5);
   const int lw_all = (int)blockIdx.x * WPC + wi;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) sw_engine_kernel(const __grid_con
 #ifdef SWB_FORCE_LONG_CHAIN                       // measurement builds only (bench/sweep.py A/B)
   constexpr bool SHORT = false;
 #else
-  constexpr bool SHORT = WPC == 4;     // one warp per scheduler: shortest dependency chain; two: fewest instructions
+  constexpr bool SHORT = WPC != 8;     // one warp per scheduler (and config 6): shortest dependency chain; two: fewest instructions
 #endif
   if constexpr (MODE == 2) engine_warp_s32<R, SLACK, false, SHORT>(P, w, lw, &sm[wi]);
   else if constexpr (MODE == 5) engine_warp_s32<R, SLACK, true, SHORT>(P, w, lw, &sm[wi]);
@@ -83,6 +86,8 @@ static const void* engine_kernel_lookup(int R, int config) {
     if constexpr (S16) {                                                         \
       if (config == 4) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 1>;  \
       if (config == 5) return (const void*)sw_engine_kernel<RR, MODE, 1, 4, 0, true>;  \
+      if constexpr (RR <= 10) { if (config == 6) return (const void*)sw_engine_kernel<RR, MODE, 1, 12>; }  \
+      if (config == 6) return nullptr;                                           \
     }                                                                            \
     return config == 1 ? (const void*)sw_engine_kernel<RR, MODE, 1, 4>           \
          : config == 2 ? (const void*)sw_engine_kernel<RR, MODE, 0, 8>           \

@@ -223,3 +223,17 @@ def test_rebased_lanes_far_above_zero_run_without_the_floor(emu, mode):
     assert want > 40000
     assert emu(a, b, 4, mode, 0, 2, 2, p) == (want, 0)
     assert emu(a, b, 2, mode, 1, 2, 1, p, hs=True) == (want, 0)
+
+
+def test_recentring_does_not_wrap_the_stand_in_boundary(emu):
+    """LT a multiple of the 256-step block, slack step, base above 30 000: lane 0 holds the stand-in for the boundary
+    value of T position LT (-30000 - open) when the band re-centres at the start of its last block; a rising base
+    used to wrap it around to +32 5xx, and the pad column scored 66 453 instead of 39 443 (on the GPU: 483 137 instead
+    of 456 586 for a 4 M x 4 M pair with 8 rows per sub-lane)."""
+    p, n = (10, -8, 7, 7), 4352
+    a = rng.random_acgt(1, 0, n)
+    b = rng.mutate(a, 1, 1, 0.04, 0.02)[:n]
+    assert len(b) == n
+    want = O.gotoh_rolling(a, b, p)
+    assert want == 39443
+    assert emu(a, b, 3, 4, 1, 3, 1, p) == (want, 0)

@@ -342,6 +342,25 @@ def test_rebased_16_bit_lanes(api, config):
         assert (info["two_sided"], info["rebased"]) == (1, 1)
 
 
+def test_recentring_with_a_stand_in_boundary_value(api):
+    """Regression (round 2): with the slack step, LT a multiple of the 256-step block and a base above 30 000, lane 0
+    holds the stand-in for the boundary value of T position LT when the band re-centres at its last block; a rising
+    base wrapped it around (4 M x 4 M, seed 2, 8 rows per sub-lane: 483 137 instead of 456 586).  Identical sequences of
+    many block-multiple lengths (score = N, analytic) and the original pair."""
+    import torch
+    ctx = api.Context(0)
+    n_max = 40960 + 256 * 48
+    a = torch.from_numpy(rng.random_acgt(77, 0, n_max).copy()).cuda()
+    for n in range(40960, n_max + 1, 256):
+        for rows in (3, 8):
+            assert ctx.score_device(a.data_ptr(), n, a.data_ptr(), n, lanes=16, rebase=1, rows=rows, config=1, two_sided=-1) == n, (n, rows)
+    n = 4000000
+    a = torch.from_numpy(rng.random_acgt(2, 0, n).copy()).cuda(); b = torch.from_numpy(rng.random_acgt(2, 1, n).copy()).cuda()
+    got = [ctx.score_device(a.data_ptr(), n, b.data_ptr(), n, lanes=16, rebase=1, rows=8, config=c, two_sided=-1) for c in (1, 3)]
+    assert got == [456586, 456586]
+    ctx.close()
+
+
 def test_rebased_lanes_refuse_unsafe_parameters(api):
     a = rng.random_acgt(531, 0, 5000)
     with pytest.raises(api.SwbError):
