@@ -1,0 +1,13 @@
+#!/bin/bash
+# Builds the chain kernels with each flag set in "$@" into a scratch copy of the library and runs bench/chain_stress.py on it.
+cd "$(dirname "$0")/.."
+NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+OBJS=$(ls build/csrc/*.o | grep -v swb_chain.o)
+cp concurrentproject_b200/lib/libswb200.so /tmp/libswb200.keep
+for flags in "$@"; do
+  echo "=== flags: $flags"
+  $NV $flags -c concurrentproject_b200/csrc/swb_chain.cu -o /tmp/swb_chain_var.o 2>/dev/null || { echo build failed; continue; }
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o concurrentproject_b200/lib/libswb200.so $OBJS /tmp/swb_chain_var.o -lpthread
+  timeout 200 python bench/chain_stress.py ${REPS:-60} 2>&1 | tail -4
+done
+cp /tmp/libswb200.keep concurrentproject_b200/lib/libswb200.so

@@ -8,6 +8,7 @@
 #include "../../include/swb200.h"
 #include "../../include/algoGPU.h"
 #include "swb_kernels.cuh"
+#include "swb_chain.cuh"
 #include "swb_batch.cuh"
 #include "swb_banded.cuh"
 
@@ -36,6 +37,7 @@ struct Settings {
   std::string dump_final_path;                  // SWB200_DUMP_FINAL: the two middle rows of a two-sided sweep
   long long batch_chunk_bytes = 0;              // SWB200_BATCH_CHUNK_BYTES: tests force many small chunks
   long long ring_min_cells = 200LL * 1000 * 1000 * 1000;   // SWB200_RING_MIN_CELLS: pairs at least this large use all devices
+  int chain = 0;                                // SWB200_CHAIN: 1 = the planner may pick the CTA-chained engine (launch config 7) by itself
 };
 std::mutex g_settings_mu;
 Settings& settings_locked() {       // caller holds g_settings_mu
@@ -50,6 +52,7 @@ Settings& settings_locked() {       // caller holds g_settings_mu
     if (const char* e = getenv("SWB200_DUMP_FINAL")) st.dump_final_path = e;
     if (const char* e = getenv("SWB200_BATCH_CHUNK_BYTES")) st.batch_chunk_bytes = std::max(1LL, atoll(e));
     if (const char* e = getenv("SWB200_RING_MIN_CELLS")) st.ring_min_cells = std::max(1LL, atoll(e));
+    if (const char* e = getenv("SWB200_CHAIN")) st.chain = atoi(e);
   }
   return st;
 }
@@ -242,6 +245,7 @@ struct swb200_ctx {
   uint64_t* d_t2 = nullptr; size_t t2_cap = 0;
   uint2* d_final = nullptr; size_t final_cap = 0; // two-sided sweep: the two middle boundary rows
   uint2* d_links = nullptr; size_t links_cap = 0;  // entries
+  uint2* d_chain = nullptr; size_t chain_cap = 0;  // CTA-chained engine (launch config 7): one full-length link per CTA
   uint2* d_ext = nullptr; size_t ext_cap = 0;      // entries
   unsigned long long* d_progress = nullptr; size_t progress_cap = 0;
   int* d_cand = nullptr; size_t cand_cap = 0;     // end-cell tracking: {H, T position, Q row} per band
@@ -422,6 +426,9 @@ struct Plan {
 // (config 2: fewest-instructions row loop) 14 / 10 / 12.5 / 15 / 11 / 14.5, times 1.5 per warp.  A band starts
 // `lag` steps after the band above it (lane skew + 48 steps of poll look-ahead + ~60 steps of L2 visibility);
 // the pair is done when the last band is.  The estimate only steers the choice of kernel, never the result.
+constexpr double kChainStepFixed = 24.0;   // cycles per step that do not depend on the rows (fitted, profiles/r02_chain_*.txt)
+constexpr double kChainLag = 130.0;        // average steps between the starts of two consecutive bands
+
 double estimate(long long LQ, long long LT, int mode, int R, int config, int sms, bool two_sided = false) {
   const int rpb = swb::rows_per_band(R, mode);
   const long long NB = (LQ + rpb - 1) / rpb;
@@ -451,8 +458,24 @@ double estimate(long long LQ, long long LT, int mode, int R, int config, int sms
 struct Plan;
 const void* kernel_for(const Plan& pl);
 
+// The CTA-chained engine (launch config 7): one band per warp, four consecutive bands per CTA.  Same model as
+// estimate(): a band starts `lag` steps after the band above it, but three of four hand-offs stay in shared memory
+// and the compute warps carry no chunk prologue.  1e300: this shape does not fit (the caller keeps the other engine).
+double estimate_chain(long long LQ, long long LT, int mode, int R, int sms, bool two_sided) {
+  if ((mode != 0 && mode != 1) || !swb::chain_kernel(mode, R)) return 1e300;
+  const int rpb = swb::rows_per_band(R, mode);
+  const long long NB = (LQ + rpb - 1) / rpb;
+  const long long NB0 = two_sided ? NB / 2 : NB, NB1 = two_sided ? NB - NB0 : 0;
+  if (two_sided && NB0 < 4) return 1e300;
+  if ((NB0 + 3) / 4 + (NB1 + 3) / 4 > sms) return 1e300;
+  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + kChainStepFixed;
+  const double lag = kChainLag;
+  const double bands = (double)std::max(NB0, NB1);
+  return ((bands - 1.0) * lag + (double)(LT + swb::kChainSkew)) * cyc_step + (two_sided ? 30000.0 : 0.0);
+}
+
 Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_options& o, int lanes, int sms,
-               bool allow_two_sided = false) {
+               bool allow_two_sided = false, bool allow_chain = false) {
   Plan pl{};
   pl.swap = o.orient ? o.orient == 2 : m > n;   // default: stripe the longer sequence across lanes
   const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
@@ -491,7 +514,19 @@ Plan make_plan(long long n, long long m, const swb200_params& p, const swb200_op
       }
     }
   }
-  if (best == 1e300) { pl.R = o.rows ? o.rows : 4; pl.config = o.config ? o.config : 1; }
+  // the CTA-chained engine: on request (config 7), or by itself when its estimate beats the best plan above
+  if (allow_chain && (o.config == swb::kChainConfig || (o.config == 0 && settings().chain > 0))) {
+    for (int ri = 0; ri < swb::kNumRowChoices; ++ri) {
+      const int R = swb::kRowChoices[ri];
+      if (o.rows && o.rows != R) continue;
+      for (int t2 = 0; t2 < 2; ++t2) {
+        if (t2 ? (!allow_two_sided || o.two_sided < 0 || LQ < 8LL * swb::rows_per_band(R, pl.mode)) : o.two_sided > 0) continue;
+        const double e = estimate_chain(LQ, LT, pl.mode, R, sms, t2 != 0);
+        if (e < best) { best = e; pl.R = R; pl.config = swb::kChainConfig; pl.two_sided = t2 != 0; }
+      }
+    }
+  }
+  if (best == 1e300) { pl.R = o.rows ? o.rows : 4; pl.config = (o.config && o.config != swb::kChainConfig) ? o.config : 1; }
   pl.ctas = o.ctas;
   return pl;
 }
@@ -531,8 +566,10 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
              const swb200_params& p, const swb200_options& o, int lanes, const uint8_t* d_lut, cudaStream_t s,
              int* score, int* status, const RingCfg* ring = nullptr, int* end3 = nullptr) {
   const int world = ring ? ring->world : 1;
-  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr || ring->root != nullptr);
-  const void* kern = kernel_for(pl);
+  const Plan pl = make_plan(n, m, p, o, lanes, c->sms * world, /*allow_two_sided=*/ring == nullptr || ring->root != nullptr,
+                            /*allow_chain=*/ring == nullptr);
+  const bool chain = pl.config == swb::kChainConfig;        // CTA-chained engine: plain 16-bit lanes, one band per warp, one GPU
+  const void* kern = chain ? swb::chain_kernel(pl.mode, pl.R) : kernel_for(pl);
   if (!kern) return fail(SWB200_ERR_ARG, "no kernel for rows=" + std::to_string(pl.R));
   const uint8_t* dq = pl.swap ? d_seq2 : d_seq1;
   const uint8_t* dt = pl.swap ? d_seq1 : d_seq2;
@@ -553,13 +590,19 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const long long LQ1 = ts ? LQ - mid : 0, NB1 = ts ? (LQ1 + rpb - 1) / rpb : 0, pad1 = NB1 * rpb - LQ1;
 
   int per_sm = 0;
-  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, 0));
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, chain ? 160 : wpc * 32, 0));
   if (per_sm < 1) return fail(SWB200_ERR_CUDA, "engine kernel does not fit on an SM");
   const long long want_warps = ts ? 2 * std::max(NB0, NB1) : NB;
   long long ctas = std::min<long long>((want_warps + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
   if (pl.ctas > 0) ctas = std::min<long long>(ctas, pl.ctas);
   ctas = std::max<long long>(ctas, ts ? 2 : 1);
   if (ring) ctas = pl.ctas > 0 ? std::min<long long>(pl.ctas, c->sms) : c->sms;   // every rank launches the same shape
+  const long long chain_ctas0 = (NB0 + 3) / 4, chain_ctas1 = (NB1 + 3) / 4;         // a chained CTA owns four consecutive bands
+  if (chain) {
+    if (ring || chain_ctas0 + chain_ctas1 > (long long)c->sms)
+      return fail(SWB200_ERR_ARG, "launch config 7 needs one band per warp on one GPU (more rows per sub-lane, or another config)");
+    ctas = chain_ctas0 + chain_ctas1;
+  }
   const int warps = (int)ctas * wpc;
   const int split = ts ? warps / 2 : 0;
 
@@ -583,6 +626,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const size_t links_need = (size_t)std::max(warps, 1) * 2 * (size_t)link_len;
   const size_t ext_need = (ts ? 4 : 2) * (size_t)ext_len;
   if ((rc = grow(c->d_links, c->links_cap, links_need, true, s))) return rc;
+  const long long chain_stride = nsteps + 64;
+  if (chain && (rc = grow(c->d_chain, c->chain_cap, (size_t)ctas * (size_t)chain_stride, true, s))) return rc;
   if (ring) {
     if ((size_t)ext_len > ring->len)
       return fail(SWB200_ERR_ARG, "ring was created for a shorter streamed sequence (max_len too small)");
@@ -607,6 +652,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   if (c->epoch > 63) {
     c->epoch = 1;
     SWB_CUDA(cudaMemsetAsync(c->d_links, 0, c->links_cap * sizeof(uint2), s));
+    if (c->d_chain) SWB_CUDA(cudaMemsetAsync(c->d_chain, 0, c->chain_cap * sizeof(uint2), s));
     if (c->d_ext) SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
   }
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
@@ -672,6 +718,24 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   }
   void* args[] = {&L};
   SWB_CUDA(cudaEventRecord(c->ev0, s));
+  if (chain) {
+    swb::ChainLaunch CL{};
+    swb::ChainParams& A = CL.a;
+    A.q_codes = P.q_codes; A.t_packed = P.t_packed; A.LQ = P.LQ; A.LT = (int)LT; A.NB = (int)NB0;
+    A.links = c->d_chain; A.link_stride = chain_stride; A.final_out = ts ? final_f : nullptr;
+    A.tag = (c->epoch << 26) | 0x5A5A5Au; A.result = c->d_result;
+    A.match = p.match; A.mismatch = p.mismatch; A.gap_init = p.gap_init; A.gap_ext = p.gap_ext;
+    A.spin_limit = cfg.spin_limit;
+    CL.split = (int)chain_ctas0;
+    if (ts) {
+      swb::ChainParams& B2 = CL.b;
+      B2 = A;
+      B2.q_codes = c->d_q2; B2.t_packed = c->d_t2; B2.LQ = NB1 * rpb; B2.NB = (int)NB1;
+      B2.links = c->d_chain + (size_t)chain_ctas0 * (size_t)chain_stride; B2.final_out = final_b;
+    }
+    void* cargs[] = {&CL};
+    SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3(160u), cargs, 0, s));
+  } else
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
   if (ts && ring) {
     // the two last bands may live on any rank: the root combines once EVERY rank's kernel has finished
@@ -888,6 +952,7 @@ int swb200_configure(const char* key, const char* value) {
   else if (k == "dump_final") st.dump_final_path = value;
   else if (k == "batch_chunk_bytes") st.batch_chunk_bytes = std::max(0LL, atoll(value));
   else if (k == "ring_min_cells") st.ring_min_cells = std::max(1LL, atoll(value));
+  else if (k == "chain") st.chain = atoi(value);
   else return fail(SWB200_ERR_ARG, "unknown setting: " + k);
   return SWB200_OK;
 }
@@ -899,11 +964,12 @@ int swb200_plan(long long n, long long m, const swb200_params* pp, const swb200_
   if (!out || n < 1 || m < 1 || sms < 1) return fail(SWB200_ERR_ARG, "bad plan arguments");
   const swb200_params p = pp ? *pp : swb200_params{1, -1, 1, 1};
   const swb200_options o = oo ? *oo : swb200_options{};
-  const Plan pl = make_plan(n, m, p, o, lanes, sms, allow_two_sided != 0);
+  const Plan pl = make_plan(n, m, p, o, lanes, sms, allow_two_sided != 0, /*allow_chain=*/allow_two_sided != 0);
   out[0] = pl.mode; out[1] = pl.R; out[2] = pl.config; out[3] = pl.two_sided ? 1 : 0;
   if (est_cycles) {
     const long long LQ = pl.swap ? m : n, LT = pl.swap ? n : m;
-    *est_cycles = estimate(LQ, LT, pl.mode, pl.R, pl.config, sms, pl.two_sided);
+    *est_cycles = pl.config == swb::kChainConfig ? estimate_chain(LQ, LT, pl.mode, pl.R, sms, pl.two_sided)
+                                                 : estimate(LQ, LT, pl.mode, pl.R, pl.config, sms, pl.two_sided);
   }
   return SWB200_OK;
 }
@@ -949,7 +1015,7 @@ void swb200_ctx_destroy(swb200_ctx* c) {
   if (!c) return;
   DeviceGuard guard;
   cudaSetDevice(c->device);
-  cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_ext);
+  cudaFree(c->d_ascii); cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_q2); cudaFree(c->d_t2); cudaFree(c->d_final); cudaFree(c->d_links); cudaFree(c->d_chain); cudaFree(c->d_ext);
   cudaFree(c->d_dirs); cudaFree(c->d_ops); cudaFree(c->d_prof); cudaFree(c->d_progress); cudaFree(c->d_cand); cudaFree(c->d_rev); cudaFree(c->d_result); cudaFree(c->d_lut);
   cudaFree(c->hb_seq1); cudaFree(c->hb_seq2); cudaFree(c->hb_off1); cudaFree(c->hb_off2); cudaFree(c->hb_len1); cudaFree(c->hb_len2);
   cudaFree(c->hb_scores); cudaFree(c->hb_qw); cudaFree(c->hb_tw); cudaFree(c->hb_ql); cudaFree(c->hb_tl);

@@ -15,9 +15,11 @@ namespace swb {
 // config 6: 12 warps per CTA (three per scheduler), slack step, short-chain row loop, at most 10 rows per
 //           sub-lane (170 registers per thread, 36 KB of shared memory): for pairs with far more bands than warps, where
 //           the schedulers and not the pipeline depth are the limit; packed 16-bit modes only
-constexpr int kNumConfigs = 6;
+// config 7: the CTA-chained engine of swb_chain.cuh (four consecutive bands per CTA handed over through shared memory,
+//           a helper warp for tables and the L2 link); plain packed 16-bit modes, one band per warp, one GPU
+constexpr int kNumConfigs = 6;      // launch configs of sw_engine_kernel; 7 is a kernel of its own
 SWB_HD int config_wpc(int config) { return config == 2 ? 8 : (config == 6 ? 12 : 4); }
-SWB_HD int config_slack(int config) { return (config == 1 || config == 4 || config == 5 || config == 6) ? 1 : 0; }
+SWB_HD int config_slack(int config) { return (config == 1 || config == 4 || config == 5 || config == 6 || config == 7) ? 1 : 0; }
 SWB_HD int config_hs(int config) { return config == 4 ? 1 : 0; }
 // steps by which the last sub-lane of a band trails the first (what a band adds to the sweep; entry slot - T position)
 SWB_HD int config_skew(int config, int mode) {
