@@ -37,7 +37,7 @@ struct Settings {
   std::string dump_final_path;                  // SWB200_DUMP_FINAL: the two middle rows of a two-sided sweep
   long long batch_chunk_bytes = 0;              // SWB200_BATCH_CHUNK_BYTES: tests force many small chunks
   long long ring_min_cells = 200LL * 1000 * 1000 * 1000;   // SWB200_RING_MIN_CELLS: pairs at least this large use all devices
-  int chain = 0;                                // SWB200_CHAIN: 1 = the planner may pick the CTA-chained engine (launch config 7) by itself
+  int chain = 1;                                // SWB200_CHAIN: 0 = the planner never picks the CTA-chained engine (launch config 7) by itself
 };
 std::mutex g_settings_mu;
 Settings& settings_locked() {       // caller holds g_settings_mu
@@ -426,9 +426,6 @@ struct Plan {
 // (config 2: fewest-instructions row loop) 14 / 10 / 12.5 / 15 / 11 / 14.5, times 1.5 per warp.  A band starts
 // `lag` steps after the band above it (lane skew + 48 steps of poll look-ahead + ~60 steps of L2 visibility);
 // the pair is done when the last band is.  The estimate only steers the choice of kernel, never the result.
-constexpr double kChainStepFixed = 24.0;   // cycles per step that do not depend on the rows (fitted, profiles/r02_chain_*.txt)
-constexpr double kChainLag = 130.0;        // average steps between the starts of two consecutive bands
-
 double estimate(long long LQ, long long LT, int mode, int R, int config, int sms, bool two_sided = false) {
   const int rpb = swb::rows_per_band(R, mode);
   const long long NB = (LQ + rpb - 1) / rpb;
@@ -468,8 +465,12 @@ double estimate_chain(long long LQ, long long LT, int mode, int R, int sms, bool
   const long long NB0 = two_sided ? NB / 2 : NB, NB1 = two_sided ? NB - NB0 : 0;
   if (two_sided && NB0 < 4) return 1e300;
   if ((NB0 + 3) / 4 + (NB1 + 3) / 4 > sms) return 1e300;
-  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + kChainStepFixed;
-  const double lag = kChainLag;
+  // fitted on one-sided sweeps of a 100 000-row Q against T of 25 000 ... 400 000 (bench/chain_fit.py, profiles/r02_chain_fit.txt):
+  // groups of 32 steps: 44.0 cycles per step at R = 3 linear, a band starts 150 steps after the band above it;
+  // groups of 16 steps: 67.9 cycles per step at R = 3 affine, 125 steps
+  const bool g32 = swb::chain_group(mode, R) == 32;
+  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + (g32 ? 23.0 : 28.0);
+  const double lag = g32 ? 150.0 : 125.0;
   const double bands = (double)std::max(NB0, NB1);
   return ((bands - 1.0) * lag + (double)(LT + swb::kChainSkew)) * cyc_step + (two_sided ? 30000.0 : 0.0);
 }

@@ -306,7 +306,10 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
             xnext = chain_lds(inbp + 4u * (k + 1));
           }
 #endif
-          if (k == G / 2) {                                          // what the NEXT group needs, read early
+#ifndef SWB_CHAIN_PF
+#define SWB_CHAIN_PF 8
+#endif
+          if (k == G - SWB_CHAIN_PF) {                               // what the NEXT group needs, read a few steps early
             have = chain_ld_nb(cnt_in);
             if (!GS) bp = chain_ld_nb(bp_word);
           }
@@ -424,8 +427,11 @@ __global__ void __launch_bounds__(160, 1) sw_chain_kernel(const __grid_constant_
     const uint32_t padw = ((uint32_t)(P.mismatch + P.gap_init) & 0xFFu) * 0x01010101u;
     for (int i = (int)threadIdx.x; i < 2 * kChainTab; i += (int)blockDim.x) sm.tab[i] = padw;
     const uint32_t nopen = pack2(-P.gap_init);
-    if (c == 0)                                                     // the side's first band: zero border above it
-      for (int i = (int)threadIdx.x; i < kChainInb + kChainGMax; i += (int)blockDim.x) sm.inbox[0][i] = nopen;
+    // every inbox starts as a zero border: the first band of a side keeps reading it; the others read entries of
+    // T positions beyond LT before (or without) their producer writing them -- harmless as long as what they find is
+    // not above a real score (stale real entries are not, uninitialised shared memory is)
+    uint32_t* const ib = &sm.inbox[0][0];
+    for (int i = (int)threadIdx.x; i < 4 * (kChainInb + kChainGMax + 4); i += (int)blockDim.x) ib[i] = nopen;
     if (threadIdx.x < 4) { sm.cnt[threadIdx.x] = 0; sm.done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) { sm.abort = 0; sm.tagw = P.tag; sm.never = 0x3fffffff; }
   }

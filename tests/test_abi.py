@@ -43,10 +43,11 @@ def test_library_is_sm100a_only_and_uses_dpx():
     so = ROOT / "concurrentproject_b200" / "lib" / "libswb200.so"
     out = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3swb16sw_engine_kernelILi4ELi0ELi1ELi4ELi0EEEvNS_12EngineLaunchE",
-                           str(so)], capture_output=True, text=True).stdout
-    for mnemonic in ("VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "PRMT", "SHFL.IDX"):
-        assert mnemonic in sass, mnemonic
+    for fun in ("_ZN3swb16sw_engine_kernelILi4ELi0ELi1ELi4ELi0ELb0EEEvNS_12EngineLaunchE",      # pair engine, affine, 4 rows
+                "_ZN3swb15sw_chain_kernelILi3ELi1EEEvNS_11ChainLaunchE"):                       # CTA-chained engine, linear, 3 rows (cfg2)
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, str(so)], capture_output=True, text=True).stdout
+        for mnemonic in ("VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIADD.16x2", "PRMT", "SHFL.IDX"):
+            assert mnemonic in sass, (fun, mnemonic)
 
 
 def test_argument_errors_need_no_gpu(lib):

@@ -233,6 +233,7 @@ def test_recentring_does_not_wrap_the_stand_in_boundary(emu):
     p, n = (10, -8, 7, 7), 4352
     a = rng.random_acgt(1, 0, n)
     b = rng.mutate(a, 1, 1, 0.04, 0.02)[:n]
+    b = np.concatenate([b, rng.random_acgt(1, 2, n - len(b))])      # LT = 4352 = 17 * 256 exactly
     assert len(b) == n
     want = O.gotoh_rolling(a, b, p)
     assert want == 39443
