@@ -325,7 +325,7 @@ def pair_record(env, args, name):
                      "frac": round(achieved / peak, 4), "traffic": ncu_traffic(name),
                      "note": f"wavefront kernel only, {k_ms:.3f} ms/launch (CUDA events on its stream); traffic = DRAM bytes per launch "
                              f"from the committed ncu capture, algorithmic input is {(n + m) // 4} bytes, "
-                             f"the boundary rows of the bands live in L2; peak = 148 SM x {f_mhz} MHz x "
+                             f"the boundary rows between CTAs stream through L2 (full-length links, partly written back); peak = 148 SM x {f_mhz} MHz x "
                              f"L={DPX_LANE_INSTR_PER_CLK_PER_SM:.0f} DPX lane-instr/clk/SM (measured, bench/intpeak.cu) x V={vwidth} / 7 "
                              "instr per cell vector (SURVEY.md 8d); not an HBM- or tensor-bound kernel"},
         "cpu_baseline": {"value": round(cpu_g, 4), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": text},
