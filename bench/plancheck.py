@@ -4,7 +4,7 @@ import sys, json, torch
 sys.path.insert(0, '.')
 from concurrentproject_b200 import api, rng
 ctx = api.Context(0)
-for n in (20000, 50000, 100000, 200000, 500000):
+for n in (5000, 20000, 50000, 100000, 150000, 200000, 250000, 500000):
     a = torch.from_numpy(rng.random_acgt(2, 0, n).copy()).cuda(); b = torch.from_numpy(rng.random_acgt(2, 1, n).copy()).cuda()
     def run(**kw):
         best = None
@@ -14,8 +14,8 @@ for n in (20000, 50000, 100000, 200000, 500000):
         return s, best
     s0, auto = run()
     res = []
-    for cfg in (1, 2, 3):
-        for R in (2, 3, 4, 6, 8, 10, 12, 14, 16):
+    for cfg in (1, 2, 3, 7):
+        for R in ((1, 2, 3, 4, 6, 8) if cfg == 7 else (2, 3, 4, 6, 8, 10, 12, 14, 16)):
             for ts in ((1, -1) if n <= 250000 else (-1,)):
                 try:
                     s, i = run(rows=R, config=cfg, two_sided=ts)

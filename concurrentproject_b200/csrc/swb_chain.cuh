@@ -262,6 +262,8 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
   __syncwarp();
 #ifdef SWB_CHAIN_PROF
   const long long pr_t0 = clock64();
+  unsigned long long pr_gt0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_gt0));
 #endif
   // boundary value of T position 0 for lane 0 (nothing was shuffled before step 0)
   if (have >= 0 && lane == 0) yold = sm->inbox[w][SKEW & (kChainInb - 1)];
@@ -401,6 +403,8 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
     if (smem_sink || !has_sink) sweep(std::false_type{}); else sweep(std::true_type{});
   }
 #ifdef SWB_CHAIN_PROF
+  if (lane == 0 && c >= 40 && c <= 42)
+    printf("chainstart cta %d warp %d band %d start_ns %llu\n", c, w, band, pr_gt0);
   if ((lane == 0 || lane == 31) && (c == 10 || c == 40))
     printf("chainprof cta %d warp %d band %d: %.1f cyc/step over %d steps, waits %lld (%.1f cyc/step), group body %.1f cyc/step, activemask and %08x partial %d\n", c, w, band,
            (double)(clock64() - pr_t0) / nsteps, nsteps, pr_waits, (double)pr_wait / nsteps, (double)pr_bp / nsteps, pr_am_and, pr_am_n);
