@@ -26,6 +26,9 @@ const void* batch_kernel(int R, int mode, int G) {
 const void* banded_kernel(int mode) {
   return mode == 0 ? (const void*)sw_banded_kernel<0> : (const void*)sw_banded_kernel<1>;
 }
+const void* banded4_kernel(int mode) {
+  return mode == 0 ? (const void*)sw_banded4_kernel<0> : (const void*)sw_banded4_kernel<1>;
+}
 const void* banded8_kernel(int mode) {
   return mode == 0 ? (const void*)sw_banded8_kernel<0> : (const void*)sw_banded8_kernel<1>;
 }
