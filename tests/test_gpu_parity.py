@@ -138,6 +138,24 @@ def test_chained_engine_is_the_default_for_config2_and_is_stable(api):
     ctx.close()
 
 
+def test_chained_engine_gives_up_instead_of_hanging(api):
+    """Every wait of the chained engine has a budget: with a budget of 3 polls the 100 000 x 100 000 pair comes back as
+    SWB200_ERR_TIMEOUT within milliseconds (no hang, no wrong score), and the next call with the normal budget is right."""
+    import torch
+    n = 100000
+    ctx = api.Context(0)
+    a = torch.from_numpy(rng.random_acgt(2, 0, n).copy()).cuda(); b = torch.from_numpy(rng.random_acgt(2, 1, n).copy()).cuda()
+    api.configure("spin_limit", 3)
+    try:
+        with pytest.raises(api.SwbError) as e:
+            ctx.score_device(a.data_ptr(), n, b.data_ptr(), n, config=7)
+        assert "TIMEOUT" in str(e.value)
+    finally:
+        api.configure("spin_limit", 40000000)
+    assert ctx.score_device(a.data_ptr(), n, b.data_ptr(), n, config=7) == 11446
+    ctx.close()
+
+
 def test_many_rounds_on_few_ctas(api):
     # force the ring to wrap: 3 CTAs, many bands
     a, b = planted(510, 20000, 0.1, 0.04)
