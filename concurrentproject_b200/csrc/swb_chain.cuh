@@ -102,6 +102,17 @@ __device__ __forceinline__ int chain_ld_nb(const int* p) {
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
   return v;
 }
+// counters through 32-bit shared addresses computed once per band (a generic-to-shared conversion inside the loop is an
+// S2R + LEA per use, and the S2R sat in the single warp's way at every loop back-edge)
+__device__ __forceinline__ int chain_ld_nb_s(uint32_t addr) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void chain_st_if_s(bool on, uint32_t addr, int v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared.s32 [%0], %1;\n\t}"
+               ::"r"(addr), "r"(v), "r"((uint32_t)on) : "memory");
+}
 // shared-memory word at a 32-bit shared address (no generic-to-shared conversion inside the loops; ptxas folds the
 // constant part of the address into the instruction)
 __device__ __forceinline__ uint32_t chain_lds(uint32_t addr) {
@@ -268,9 +279,13 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
   // boundary value of T position 0 for lane 0 (nothing was shuffled before step 0)
   if (have >= 0 && lane == 0) yold = sm->inbox[w][SKEW & (kChainInb - 1)];
 
-  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(&sm->tab[0]);
-  const uint32_t inb_s = (uint32_t)__cvta_generic_to_shared(&sm->inbox[w][0]);
-  const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(&sm->inbox[(w + 1) & 3][0]);
+  uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(&sm->tab[0]);
+  uint32_t inb_s = (uint32_t)__cvta_generic_to_shared(&sm->inbox[w][0]);
+  uint32_t out_s = (uint32_t)__cvta_generic_to_shared(&sm->inbox[(w + 1) & 3][0]);
+  asm volatile("" : "+r"(tab_s), "+r"(inb_s), "+r"(out_s));          // computed once, not once per group
+  uint32_t cnt_in_s = (uint32_t)__cvta_generic_to_shared(cnt_in), cnt_out_s = (uint32_t)__cvta_generic_to_shared(cnt_out);
+  uint32_t done_me_s = (uint32_t)__cvta_generic_to_shared(done_me), bp_s = (uint32_t)__cvta_generic_to_shared(bp_word);
+  asm volatile("" : "+r"(cnt_in_s), "+r"(cnt_out_s), "+r"(done_me_s), "+r"(bp_s));
   auto sweep = [&](auto GS_) {
     // GS (global sink: warp 3 / a side's last band) stores its {value, tag} entry inside the step, as sw_engine_kernel
     // does -- global stores cannot alias the shared-memory loads.  Shared sinks collect the group's values in
@@ -281,7 +296,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
     for (;;) {
       bool go_on;
       do {      // ---- one group of G steps per trip; ONE branch per group when nothing has to be waited for
-        chain_st_if(lane == 0, done_me, i0);
+        chain_st_if_s(lane == 0, done_me_s, i0);
         const uint32_t tabp = tab_s + 4u * ((i0 - SK * lane) & (kChainTab - 1));
         const uint32_t inbp = inb_s + 4u * ((i0 + SKEW + 1) & (kChainInb - 1));  // lane 31 ships T position i + 1 = producer step i + 1 + SKEW
         uint32_t xq[GS ? 1 : G];
@@ -312,8 +327,8 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
 #define SWB_CHAIN_PF 8
 #endif
           if (k == G - SWB_CHAIN_PF) {                               // what the NEXT group needs, read a few steps early
-            have = chain_ld_nb(cnt_in);
-            if (!GS) bp = chain_ld_nb(bp_word);
+            have = chain_ld_nb_s(cnt_in_s);
+            if (!GS) bp = chain_ld_nb_s(bp_s);
           }
 #ifdef SWB_CHAIN_PROF
           if (k == 3 || k == 12) { const unsigned am = __activemask(); pr_am_and &= am; pr_am_n += (am != 0xffffffffu); }
@@ -372,7 +387,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
 #pragma unroll
           for (int k = 0; k < G; k += 4) chain_st4_shared(twice, o + 4u * (kChainInb + k), xq[k], xq[k + 1], xq[k + 2], xq[k + 3]);
           chain_fence();
-          chain_st_if(emit, cnt_out, i0 + G);
+          chain_st_if_s(emit, cnt_out_s, i0 + G);
         }
 #ifdef SWB_CHAIN_PROF
         pr_bp += clock64() - tg0;
