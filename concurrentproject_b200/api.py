@@ -119,6 +119,19 @@ def configure(key: str, value) -> None:
         raise SwbError(rc, "swb200_configure")
 
 
+def plan(n: int, m: int, params: Sequence[int] = DEFAULT_PARAMS, lanes: int = 16, sms: int = 148, allow_two_sided: bool = True, **options) -> dict:
+    """What the planner would run for an n x m pair on `sms` SMs in all (swb200_plan; needs no GPU): mode, rows per
+    sub-lane, launch config (7 = the CTA-chained engine), two-sided sweep, estimated cycles.  lanes: 16 packed 16-bit,
+    17 packed 16-bit re-based, 32 = 32-bit lanes."""
+    p, o = _params(params), _options(**options)
+    out = (C.c_int * 4)()
+    est = C.c_double(0.0)
+    rc = _lib.load().swb200_plan(n, m, C.byref(p), C.byref(o), lanes, sms, int(allow_two_sided), out, C.byref(est))
+    if rc != 0:
+        raise SwbError(rc, "swb200_plan")
+    return {"mode": out[0], "rows": out[1], "config": out[2], "two_sided": out[3], "est_cycles": est.value}
+
+
 def last_run(ctx: Optional["Context"] = None) -> dict:
     info = RunInfo()
     rc = _lib.load().swb200_last_run(ctx.handle if ctx else None, C.byref(info))

@@ -40,8 +40,13 @@ typedef struct {
 typedef struct {
   int lanes;       /* 0 auto (packed 16-bit, 32-bit re-run if the score leaves the s16 range), 16, 32 */
   int rows;        /* R: DP rows per sub-lane, one of 1,2,3,4,6,8,10,12,14,16 (batch kernel: 2,4,6,8,10,12,16); 0 auto */
-  int config;      /* 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA), 3 = one, no slack step,
-                      4 = 1 plus a slack step inside each thread (16-bit lanes only; measurement variant) */
+  int config;      /* pair engine: 0 auto, 1 = one warp per scheduler (4 warps/CTA, slack step), 2 = two (8 warps/CTA), 3 = one, no
+                      slack step; measurement variants for packed 16-bit lanes: 4 = 1 plus a slack step inside each thread,
+                      5 = 1 with the boundary chunk fetched by cp.async.bulk + mbarrier, 6 = 12 warps/CTA (rows <= 10);
+                      7 = the CTA-chained engine (csrc/swb_chain.cuh: one band per warp, four consecutive bands per CTA handed
+                      over through shared memory; plain 16-bit lanes, one GPU, rows 1,2,3,4,6,8) -- what "auto" picks for
+                      fill-dominated pairs such as 100 000 x 100 000.
+                      banded calls: 0 = 4 threads per pair (default), 8 = 8 threads per pair, 16 = 16 threads per pair */
   int ctas;        /* thread blocks (<= co-resident limit); 0 auto */
   int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
   int orient;      /* 0 auto (stripe the longer sequence across lanes), 1 = stripe seq1, 2 = stripe seq2 */
@@ -71,7 +76,8 @@ SWB200_API int swb200_device_count(void);
  *   "dump_final" (SWB200_DUMP_FINAL)  file receiving the two middle boundary rows of a two-sided sweep
  *   "batch_chunk_bytes" (SWB200_BATCH_CHUNK_BYTES)  chunk size of the host batch calls' copy/compute pipeline (0 = default)
  *   "ring_min_cells" (SWB200_RING_MIN_CELLS)  host-buffer pairs with at least this many cells use all devices chosen
- *                                     with swb200_set_devices (default 2e11) */
+ *                                     with swb200_set_devices (default 2e11)
+ *   "chain" (SWB200_CHAIN)            "0": the planner never picks the CTA-chained engine (launch config 7) by itself */
 SWB200_API int swb200_configure(const char* key, const char* value);
 
 /* Diagnostic (needs no GPU): the kernel variant the planner picks for an n x m pair on `sms` SMs in all (148 per B200):
