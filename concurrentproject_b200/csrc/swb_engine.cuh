@@ -406,8 +406,11 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
       // Re-based lanes far above zero: the clamp at the zero floor cannot bind (floorw is then the stand-in -30000, and
       // every live value is within +-20000 of the base or the range check above fires and the host repeats in 32 bit),
       // so this block's steps run without it.  Every band starts at base 0, i.e. with the clamp.
-      // (linear-gap kernels only: measured -3.6 % on cfg3; the affine kernel got 3 % SLOWER with a second copy of its larger loop)
-      const bool nofloor = RB && MODE == 1 && base > 30000 && !(P.dbg & 4);
+      // (linear-gap kernels only: measured -3.6 % on cfg3; the affine kernel got 3 % SLOWER with a second copy of its larger loop.
+      //  And only in the fewest-instructions row loop of two warps per scheduler: in the short-chain loop the clamp rides on a
+      //  VIMNMX3 and dropping it saves a VIADD on the idle pipe, while the second copy of the loop costs a single warp its
+      //  instruction cache -- the 8-GPU ring, one warp per scheduler, went from 375 to 448 ms on the ranks whose bands sit above 30000)
+      const bool nofloor = RB && MODE == 1 && !SHORT && base > 30000 && !(P.dbg & 4);
       // every boundary entry of the steps before this block has been read: tell the producer (ring back-pressure)
       if (lane == 0) st_progress(my_progress, (unsigned long long)(sbase + i8 + SLACK));
       // (c) ring back-pressure: never overwrite an entry the consumer has not read yet
@@ -603,7 +606,7 @@ SWB_HD void engine_warp_s16(const EngineParams& P, const WarpCtx& w, int lw, War
         if (spec) epref = ld_entry(spec_e);
         if (RB && spec) bpref = ld_entry(spec_b);
         };
-        if (RB && nofloor) {                  // warp-uniform, constant over a block of 256 steps
+        if (RB && MODE == 1 && !SHORT && nofloor) {   // warp-uniform, constant over a block of 256 steps
 #pragma unroll (kU)
           for (int k = 0; k < kChunk / 2; ++k) step(k, std::false_type{});
           mid_chunk();
