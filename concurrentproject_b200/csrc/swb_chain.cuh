@@ -6,15 +6,19 @@
 // sweep (profiles/r02_cfg2_base_stalls.json: per-chunk code 15 %, boundary waits 13 %):
 //
 //   * a CTA is four compute warps that own four CONSECUTIVE bands, plus one helper warp.  The bottom boundary row of
-//     warp w goes straight into the shared-memory inbox of warp w+1 (one generic 8-byte store per step by lane 31, the
-//     same instruction that writes the L2 link entry in warp 3), and a step counter in shared memory says how far it is.
-//     Three of four hand-offs no longer cross L2: a band starts ~125 steps after the band above it instead of 168.
+//     warp w goes straight into the shared-memory inbox of warp w+1: lane 31 keeps the values of a group of steps in
+//     registers and stores them after the group (predicated 16-byte stores, a CTA fence, then a step counter the
+//     consumer polls).  Three of four hand-offs never leave the SM.  Warp 3 (and the last band of a side) stores
+//     tagged 8-byte entries to a full-length link in L2, inside the step, as sw_engine_kernel does.
 //   * the helper warp does what the compute warps' chunk prologue did: it expands the streamed sequence into the
 //     CTA's ring of 4-byte substitution tables (one ring for all four warps), polls the L2 link of the CTA above,
-//     validates the tagged entries and stages them in warp 0's inbox.  It shares a scheduler with one compute warp
-//     and fills the issue slots that warp leaves empty.
-//   * what is left in a compute warp between two groups of 16 steps: one compare of a prefetched counter, one
-//     store of its own progress, two address computations.
+//     validates the tagged entries and stages them in warp 0's inbox.  It shares a scheduler with one compute warp,
+//     fills issue slots that warp leaves empty and sleeps when it has nothing to do.
+//   * what is left in a compute warp between two groups of 32 (linear, rows <= 3) or 16 steps: ONE conditional branch
+//     (the loop back-edge, on a counter and a back-pressure word read a few steps earlier), one predicated store of its
+//     own progress, two address computations.  A single warp per scheduler pays 20-30 cycles per branch.
+//   Measured on BASELINE config 2 (profiles/r02_chain_experiments.txt, r02_chain_fit.txt): 44.0 cycles per step and 150
+//   steps between the starts of consecutive bands (pair engine: 56.6 and 159): 4.08 -> 3.11 ms.
 //
 // Scope: plain packed 16-bit lanes (engine modes 0 and 1), one band per warp (bands <= 4 * CTAs), one GPU, with or
 // without the two-sided sweep.  Everything else (re-based lanes, several rounds, the GPU ring, 32-bit lanes) stays
@@ -65,7 +69,7 @@ struct ChainLaunch {
 struct ChainSmem {
   uint32_t tab[2 * kChainTab];            // substitution tables per T position, filled by the helper warp
   uint32_t inbox[4][kChainInb + kChainGMax + 4]; // per compute warp: boundary values from the band above, slot = producer step mod ring;
-                                          // the first group is kept twice (a reader's 16 slots may run over the end)
+                                          // the first group is kept twice (a reader's group of slots may run over the end)
   int cnt[4];                             // producer steps completed for warp w's inbox (w = 0: staged by the helper, table included)
   int done[4];                            // compute warp w has finished every step before this one
   int abort;
@@ -81,29 +85,20 @@ __device__ __forceinline__ int chain_ld(const int* p) {
 __device__ __forceinline__ void chain_st(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-// The 16 boundary values of a group of steps leave lane 31 together, after the group: stores inside the step sequence
+// The boundary values of a group of steps leave lane 31 together, after the group: stores inside the step sequence
 // would pin every shared-memory load behind them (ptxas cannot tell the inbox from the table ring) and cost 9 cycles
-// per step in its schedule.  Shared-memory sink: four 16-byte stores of bare values; global sink: eight of {value, tag}.
-// (predicated, not branched: only lane 31 stores, and a divergent region between two groups costs a single warp dearly)
+// per step in its schedule.  16-byte stores of bare values, predicated, not branched: only lane 31 stores, and a
+// divergent region between two groups costs a single warp dearly.
 __device__ __forceinline__ void chain_st4_shared(bool on, uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
                ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"((uint32_t)on));
 }
-__device__ __forceinline__ void chain_st_if(bool on, int* p, int v) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared.s32 [%0], %1;\n\t}"
-               ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v), "r"((uint32_t)on) : "memory");
-}
 __device__ __forceinline__ void st_entry_gpu(uint2* p, uint32_t value, uint32_t tag) {
   asm volatile("st.global.relaxed.gpu.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(value), "r"(tag));
 }
-// counter read with no compiler barrier around it (the value is only compared a group later)
-__device__ __forceinline__ int chain_ld_nb(const int* p) {
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-  return v;
-}
 // counters through 32-bit shared addresses computed once per band (a generic-to-shared conversion inside the loop is an
-// S2R + LEA per use, and the S2R sat in the single warp's way at every loop back-edge)
+// S2R + LEA per use, and the S2R sat in the single warp's way at every loop back-edge); no compiler barrier around the
+// load: its value is only compared at the end of the group
 __device__ __forceinline__ int chain_ld_nb_s(uint32_t addr) {
   int v;
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -260,7 +255,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
   uint32_t best0 = 0, best1 = 0;
 
   // Between two groups of steps a compute warp does ONE compare-and-branch (to the out-of-line wait): the input counter
-  // and the back-pressure word the next group needs are read in the middle of the current group.  (A single warp per
+  // and the back-pressure word the next group needs are read a few steps before the end of the current group.  (A single warp per
   // scheduler pays 20-30 cycles for every branch; the first version of this loop had six per group and spent 260
   // cycles there.)  The flavour of the sink is a template parameter of the whole loop, not a branch per group.
   const int limit = w == 0 ? 0x3fffffff : LT + SKEW;      // warps 1-3: the band above stops at LT + SKEW; warp 0 also waits
