@@ -657,7 +657,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     if (c->d_ext) SWB_CUDA(cudaMemsetAsync(c->d_ext, 0, c->ext_cap * sizeof(uint2), s));
   }
   SWB_CUDA(cudaMemsetAsync(c->d_progress, 0, ((size_t)warps + 4) * sizeof(unsigned long long), s));
-  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 12 * sizeof(int), s));    // [0] score, [1] status, [3..8] timeout post-mortem, [11] protocol-checker mismatches
 
   const bool generic = pl.mode == 5 || pl.mode == 7 || pl.mode == 9 || pl.mode == 11;       // raw bytes straight from the caller's buffers, nothing to encode
   const int eb = (int)std::min<long long>(std::max<long long>(LQ / (16 * 256), 1), 4LL * c->sms);
@@ -756,7 +756,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
     c->info.aux_launches += 1;
   }
   SWB_CUDA(cudaEventRecord(c->ev1, s));
-  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 10 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  SWB_CUDA(cudaMemcpyAsync(c->h_result, c->d_result, 12 * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (track) SWB_CUDA(cudaMemcpyAsync(c->h_result + 24, c->d_result + 24, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
   SWB_CUDA(cudaStreamSynchronize(s));
   if (track) { end3[0] = c->h_result[24]; end3[1] = c->h_result[25]; end3[2] = c->h_result[26]; }
@@ -764,6 +764,8 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   SWB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   *score = c->h_result[0];
   *status = c->h_result[1];
+  if (c->h_result[10] != 0)        // only a -DSWB_CHAIN_CHECK build of swb_chain.cu counts here (bench/chain_check.sh)
+    fprintf(stderr, "chaincheck: %d x 1024 steps checked (32 table reads + 1 inbox read each), %d mismatches, score %d\n", c->h_result[10], c->h_result[11], c->h_result[0]);
   if (ts && !ring && !cfg.dump_final_path.empty()) {          // debugging aid: the two middle boundary rows as the kernels wrote them
     std::vector<uint2> h(4 * (size_t)ext_len);
     cudaMemcpy(h.data(), c->d_final, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
@@ -1326,7 +1328,7 @@ static int batch_pack_impl(swb200_ctx* c, const unsigned char* d_seq1, const lon
     SWB_CUDA(cudaMalloc(&b->q_len, np * sizeof(int)));
     SWB_CUDA(cudaMalloc(&b->t_len, np * sizeof(int)));
   }
-  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), s));
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 12 * sizeof(int), s));    // [0] score, [1] status, [3..8] timeout post-mortem, [11] protocol-checker mismatches
   if (npairs > 0) {
     const long long total = npairs * (b->q_stride + b->t_stride);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);

@@ -26,13 +26,18 @@
 // per-anti-diagonal launches (cudaSmithM.cu:87-189, SmithDiagonalGPU.cu:40-67).
 #pragma once
 #include "swb_engine.cuh"
-#ifdef SWB_CHAIN_PROF
+#if defined(SWB_CHAIN_PROF) || defined(SWB_CHAIN_CHECK)
 #include <cstdio>
 #endif
 
 namespace swb {
 
 constexpr int kChainConfig = 7;
+#ifdef SWB_CHAIN_CHECK_BREAK            // negative control of the protocol checker: every compute warp starts a group this many
+constexpr int kChainCheckBreak = SWB_CHAIN_CHECK_BREAK;    // entries before its inputs are complete -- the checker must report it
+#else
+constexpr int kChainCheckBreak = 0;
+#endif
 constexpr int kChainGMax = 32;       // steps between two looks at the hand-off counters: 32 for the smallest step loops, else 16
 #ifdef SWB_CHAIN_G
 SWB_HD constexpr int chain_group(int, int) { return SWB_CHAIN_G; }
@@ -75,6 +80,14 @@ struct ChainSmem {
   int abort;
   uint32_t tagw;                          // P.tag, read back through shared memory so that it lives in a register (see chain_compute)
   int never;                              // 0x3fffffff: the back-pressure word of a warp whose sink is not a shared-memory inbox
+#ifdef SWB_CHAIN_CHECK
+  // Protocol checker (bench/chain_variants.sh "-DSWB_CHAIN_CHECK"; compute-sanitizer is closed on this GPU pool): next to
+  // every inbox slot the producer step it holds, next to every table slot its T position.  Every read of the step loop
+  // checks that it found the entry it expects -- a read ahead of the producer finds an older step, a producer that
+  // overwrites an unread slot a newer one.  Mismatches are counted in result[11] and the first few printed.
+  unsigned short inbox_step[4][kChainInb + kChainGMax + 4];     // low 16 bits (the rings are far shorter than 65536 entries;
+  unsigned short tab_pos[2 * kChainTab];                        //  static shared memory is full otherwise)
+#endif
 };
 
 __device__ __forceinline__ int chain_ld(const int* p) {
@@ -170,6 +183,10 @@ static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem
       const uint32_t w = table_word(code, padw, flip);
       sm->tab[q & (kChainTab - 1)] = w;
       sm->tab[(q & (kChainTab - 1)) + kChainTab] = w;
+#ifdef SWB_CHAIN_CHECK
+      sm->tab_pos[q & (kChainTab - 1)] = (unsigned short)q;
+      sm->tab_pos[(q & (kChainTab - 1)) + kChainTab] = (unsigned short)q;
+#endif
       tab_pos += 32;
       tw = tab_pos < LT ? ld_early_u64(tp + (tab_pos >> 5)) : 0ull;
       progress = true;
@@ -185,6 +202,10 @@ static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem
         const int slot = (p + kChainSkew) & (kChainInb - 1);
         sm->inbox[0][slot] = e.x;
         if (slot < kChainGMax) sm->inbox[0][slot + kChainInb] = e.x;
+#ifdef SWB_CHAIN_CHECK
+        sm->inbox_step[0][slot] = (unsigned short)(p + kChainSkew);
+        if (slot < kChainGMax) sm->inbox_step[0][slot + kChainInb] = (unsigned short)(p + kChainSkew);
+#endif
       }
       if (n > 0) { bnd_pos += n; progress = true; }
     }
@@ -309,6 +330,18 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
         for (int k = 0; k < G; ++k) {
           const uint32_t Tlo = Tnext;
           const uint32_t xin = xnext;
+#ifdef SWB_CHAIN_CHECK
+          {
+            const int pos = i0 + k - SK * lane;                       // the T position whose table word is in Tlo
+            const int got_pos = sm->tab_pos[((i0 - SK * lane) & (kChainTab - 1)) + k];
+            if (pos >= 0 && got_pos != (pos & 0xffff) && atomicAdd(result + 11, 1) < 8)
+              printf("chaincheck TABLE cta %d warp %d lane %d step %d: expected position %d, slot holds %d\n", c, w, lane, i0 + k, pos, got_pos);
+            const int pstep = i0 + k + 1 + SKEW;                      // the producer step whose value is in xin
+            const int got_step = sm->inbox_step[w][((i0 + SKEW + 1) & (kChainInb - 1)) + k];
+            if (last_lane && band > 0 && pstep < LT + SKEW && got_step != (pstep & 0xffff) && atomicAdd(result + 11, 1) < 8)
+              printf("chaincheck INBOX cta %d warp %d step %d: expected producer step %d, slot holds %d\n", c, w, i0 + k, pstep, got_step);
+          }
+#endif
 #ifdef SWB_CHAIN_X_NOLDS                                             // timing experiment only (wrong scores)
           Tnext = Tnext * 5u + 1u;
           xnext = xnext ^ Tnext;
@@ -381,6 +414,12 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
           const bool twice = emit && (i0 & (kChainInb - 1)) == 0;
 #pragma unroll
           for (int k = 0; k < G; k += 4) chain_st4_shared(twice, o + 4u * (kChainInb + k), xq[k], xq[k + 1], xq[k + 2], xq[k + 3]);
+#ifdef SWB_CHAIN_CHECK
+          if (emit) {
+            unsigned short* const st = &sm->inbox_step[(w + 1) & 3][i0 & (kChainInb - 1)];
+            for (int k = 0; k < G; ++k) { st[k] = (unsigned short)(i0 + k); if ((i0 & (kChainInb - 1)) == 0) st[kChainInb + k] = (unsigned short)(i0 + k); }
+          }
+#endif
           chain_fence();
           chain_st_if_s(emit, cnt_out_s, i0 + G);
         }
@@ -390,7 +429,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
         // the next group: lane 31 reads producer steps up to i0 + G + SKEW, and (shared sink) the band below must have
         // read what this warp's stores of that group overwrite
         i0 += G;
-        const int need_full = i0 + G + 1 + SKEW;
+        const int need_full = i0 + G + 1 + SKEW - kChainCheckBreak;
         const int need = need_full < limit ? need_full : limit;
         go_on = i0 < nsteps && have >= need && (GS || bp >= i0 + G - (kChainInb - 64));
       } while (go_on);
@@ -399,7 +438,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
 #ifdef SWB_CHAIN_PROF
         const long long t0 = clock64();
 #endif
-        const int need_full = i0 + G + 1 + SKEW;
+        const int need_full = i0 + G + 1 + SKEW - kChainCheckBreak;
         have = chain_slow(cnt_in, need_full < limit ? need_full : limit, bp_word, GS ? 0 : i0 + G - (kChainInb - 64), spin_limit, sm, result);
         __syncwarp();
 #ifdef SWB_CHAIN_PROF
@@ -418,6 +457,9 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
   if ((lane == 0 || lane == 31) && (c == 10 || c == 40))
     printf("chainprof cta %d warp %d band %d: %.1f cyc/step over %d steps, waits %lld (%.1f cyc/step), group body %.1f cyc/step, activemask and %08x partial %d\n", c, w, band,
            (double)(clock64() - pr_t0) / nsteps, nsteps, pr_waits, (double)pr_wait / nsteps, (double)pr_bp / nsteps, pr_am_and, pr_am_n);
+#endif
+#ifdef SWB_CHAIN_CHECK
+  if (lane == 0 && have >= 0) atomicAdd(result + 10, nsteps >> 10);   // reads checked by this warp, in units of 1024 steps (33 reads per step)
 #endif
   if (lane == 0) chain_st(done_me, 0x3fffffff);
   const int m = __reduce_max_sync(0xffffffffu, hi_half_max(max16x2(best0, best1)));
@@ -446,6 +488,10 @@ __global__ void __launch_bounds__(160, 1) sw_chain_kernel(const __grid_constant_
     // not above a real score (stale real entries are not, uninitialised shared memory is)
     uint32_t* const ib = &sm.inbox[0][0];
     for (int i = (int)threadIdx.x; i < 4 * (kChainInb + kChainGMax + 4); i += (int)blockDim.x) ib[i] = nopen;
+#ifdef SWB_CHAIN_CHECK
+    for (int i = (int)threadIdx.x; i < 4 * (kChainInb + kChainGMax + 4); i += (int)blockDim.x) (&sm.inbox_step[0][0])[i] = 0xffff;
+    for (int i = (int)threadIdx.x; i < 2 * kChainTab; i += (int)blockDim.x) sm.tab_pos[i] = 0xffff;
+#endif
     if (threadIdx.x < 4) { sm.cnt[threadIdx.x] = 0; sm.done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) { sm.abort = 0; sm.tagw = P.tag; sm.never = 0x3fffffff; }
   }
