@@ -1407,9 +1407,10 @@ static int launch_banded_score(swb200_ctx* c, const BatchView& v, int band_lo, c
   // 16 threads per pair with two (options.config = 16, kept for comparison)
   // three layouts: 4 threads per pair with eight register sets each (the default: fewest shuffles and loads per cell),
   // 8 threads with four (options.config = 8) and 16 threads with two (options.config = 16), both kept for comparison
-  const bool wide = o.config == 16, mid = o.config == 8;
-  const void* kern = wide ? swb::banded_kernel(mode) : (mid ? swb::banded8_kernel(mode) : swb::banded4_kernel(mode));
-  const int threads = wide ? 256 : (mid ? 128 : 64), pairs_per_cta = 16;
+  // (options.config = 2: two threads with sixteen sets)
+  const bool wide = o.config == 16, mid = o.config == 8, two = o.config == 2;
+  const void* kern = wide ? swb::banded_kernel(mode) : (mid ? swb::banded8_kernel(mode) : (two ? swb::banded2_kernel(mode) : swb::banded4_kernel(mode)));
+  const int threads = wide ? 256 : (mid ? 128 : (two ? 32 : 64)), pairs_per_cta = 16;
   // several CTAs of 34-35 KB static shared memory per SM: ask for the large shared-memory carve-out
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   swb::BandedParams P{};
@@ -1422,7 +1423,7 @@ static int launch_banded_score(swb200_ctx* c, const BatchView& v, int band_lo, c
   const long long ctas = std::max<long long>(1, std::min<long long>((v.npairs + pairs_per_cta - 1) / pairs_per_cta, (long long)c->sms * per_sm));
   void* args[] = {&P};
   SWB_CUDA(cudaLaunchKernel(kern, dim3((unsigned)ctas), dim3((unsigned)threads), args, 0, s));
-  info->lanes = 16; info->linear = mode == 1; info->rows = 0; info->config = wide ? 216 : (mid ? 208 : 204); info->ctas = (int)ctas;
+  info->lanes = 16; info->linear = mode == 1; info->rows = 0; info->config = wide ? 216 : (mid ? 208 : (two ? 202 : 204)); info->ctas = (int)ctas;
   info->warps = (int)ctas * (threads / 32); info->bands = swb::kBandWidth; info->engine_launches += 1;
   return SWB200_OK;
 }

@@ -54,6 +54,14 @@ SWB_HD uint32_t packed_code(const uint64_t* words, int pos, int len) {
   return (pos >= 0 && pos < len) ? (uint32_t)(words[pos >> 5] >> (2 * (pos & 31))) & 3u : 4u;
 }
 
+// word i of a pair's packed sequence, the index clamped to the pair's words (0 for an empty layout)
+SWB_HD uint64_t packed_word(const uint64_t* words, long long stride, int i) {
+  const long long k = i < 0 ? 0 : (i < stride ? i : stride - 1);
+  return stride > 0 ? words[k] : 0ull;
+}
+// 64 bits starting at bit sh (0 .. 62) of the 128-bit value hi:lo
+SWB_HD uint64_t funnel64(uint64_t lo, uint64_t hi, int sh) { return (lo >> sh) | ((hi << 1) << (63 - sh)); }
+
 template <int MODE>
 SWB_HD void banded_warp(const BandedParams& P, const WarpCtx& w, long long warp_id, long long num_warps, BandedWarpSmem* sm) {
   const int lane = w.lane;
@@ -396,9 +404,9 @@ SWB_HD void banded_warpS(const BandedParams& P, const WarpCtx& w, long long warp
 #pragma unroll
     for (int k = 0; k < S; ++k) { Ho[k] = nopen; E[k] = nopen; F[k] = nopen; }
     uint32_t best = 0;
-    const int Y0 = I0 - H2 * u - 1, X0 = J0 + H2 * u - 1;
 
-    // ---- rings: everything pad, then selectors for rows [Yc-32, Yc) and tables for columns [Xc, Xc+32) of chunk 0
+    // ---- rings (slot of row y: (y - Yc0) & 127, of column x: (x - Xc0) & 127 -- a chunk's 32 new entries never wrap):
+    // everything pad, then selectors for rows [Yc0-32, Yc0) and tables for columns [Xc0, Xc0+32)
     const int Yc0 = I0 - 1, Xc0 = J0 - 1;                                  // thread 0's positions at h = 0
     w.sync();
     for (int k = u; k < 2 * kBandRing; k += TP) { tab[k] = padw; sel[k] = padsel; }
@@ -406,27 +414,78 @@ SWB_HD void banded_warpS(const BandedParams& P, const WarpCtx& w, long long warp
     for (int k = u; k < kChunk; k += TP) {
       const int y = Yc0 - kChunk + k;
       const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 16, m));
-      sel[y & (kBandRing - 1)] = sv; sel[(y & (kBandRing - 1)) + kBandRing] = sv;
+      sel[(kBandRing - kChunk) + k] = sv; sel[(kBandRing - kChunk) + k + kBandRing] = sv;
       const int x = Xc0 + k;
       const uint32_t tv = table_word(packed_code(aw, x, n), padw, flip);
-      tab[x & (kBandRing - 1)] = tv; tab[(x & (kBandRing - 1)) + kBandRing] = tv;
+      tab[k] = tv; tab[k + kBandRing] = tv;
     }
-
+    // Rolling 32-symbol windows of the packed sequences (64 bits each), so that a chunk whose new rows and columns lie
+    // inside the sequences costs ONE 64-bit load per sequence, issued a chunk ahead, instead of 24 guarded ones per thread
+    // (the refill was 39 % of this kernel's stall samples, most of them waiting for those loads):
+    //   RA = rows [Yc-16, Yc+16) of the coming chunk, RN = the same for the chunk after it, TC = columns [Xc+32, Xc+64).
+    // Word indices are clamped to the pair's words: a window that overlaps the outside holds garbage there and is not
+    // used (such chunks take the guarded per-symbol path below).
+    const int wr_i = (Yc0 - 16) >> 5, wr_sh = 2 * ((Yc0 - 16) & 31);
+    const int wc_i = (Xc0 + kChunk) >> 5, wc_sh = 2 * ((Xc0 + kChunk) & 31);
+    uint64_t RA, RN, r_last, TC, c_last;
+    {
+      const uint64_t r0 = packed_word(bw, P.b_stride, wr_i), r1 = packed_word(bw, P.b_stride, wr_i + 1);
+      r_last = packed_word(bw, P.b_stride, wr_i + 2);
+      RA = funnel64(r0, r1, wr_sh); RN = funnel64(r1, r_last, wr_sh);
+      const uint64_t c0 = packed_word(aw, P.a_stride, wc_i);
+      c_last = packed_word(aw, P.a_stride, wc_i + 1);
+      TC = funnel64(c0, c_last, wc_sh);
+    }
+    const int su = 2 * H2 * u;                                             // this thread's entries: k = H2 u + j + 16 i (the offsets
+                                                                           // the step loop reads with: no bank conflicts)
     for (int c = 0; c < nchunks; ++c) {
       // ---- this chunk reads rows [Yc-16, Yc+32) and columns [Xc, Xc+64): add rows [Yc, Yc+32), columns [Xc+32, Xc+64)
       const int Yc = Yc0 + c * kChunk, Xc = Xc0 + c * kChunk;
-      for (int k = u; k < kChunk; k += TP) {
-        const int y = Yc + k;
-        const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 16, m));
-        sel[y & (kBandRing - 1)] = sv; sel[(y & (kBandRing - 1)) + kBandRing] = sv;
-        const int x = Xc + kChunk + k;
-        const uint32_t tv = table_word(packed_code(aw, x, n), padw, flip);
-        tab[x & (kBandRing - 1)] = tv; tab[(x & (kBandRing - 1)) + kBandRing] = tv;
+      const uint64_t r_new = packed_word(bw, P.b_stride, wr_i + c + 3);    // consumed at the end of the chunk
+      const uint64_t c_new = packed_word(aw, P.a_stride, wc_i + c + 2);
+      uint32_t* const selw = sel + ((c * kChunk) & (kBandRing - 1));
+      uint32_t* const tabw = tab + (((c + 1) * kChunk) & (kBandRing - 1));
+      if (Yc >= 16 && Yc + kChunk <= m) {
+        const uint32_t a_lo = (uint32_t)RA, b_lo = (uint32_t)(RA >> 32), b_hi = (uint32_t)RN;   // rows y - 16: RA; rows y: RA.hi, RN.lo
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t wb = (i ? b_hi : b_lo) >> su, wa = (i ? b_lo : a_lo) >> su;
+#pragma unroll
+          for (int j = 0; j < H2; ++j) {
+            const uint32_t sv = 0xC480u + ((wb >> (2 * j)) & 3u) * 0x11u + ((wa >> (2 * j)) & 3u) * 0x1100u;   // = mk_sel16 of two real codes
+            selw[H2 * u + j + 16 * i] = sv; selw[H2 * u + j + 16 * i + kBandRing] = sv;
+          }
+        }
+      } else {
+        for (int k = u; k < kChunk; k += TP) {
+          const int y = Yc + k;
+          const uint32_t sv = mk_sel16(packed_code(bw, y, m), packed_code(bw, y - 16, m));
+          selw[k] = sv; selw[k + kBandRing] = sv;
+        }
       }
+      if (Xc + kChunk >= 0 && Xc + 2 * kChunk <= n) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t wt = (i ? (uint32_t)(TC >> 32) : (uint32_t)TC) >> su;
+#pragma unroll
+          for (int j = 0; j < H2; ++j) {
+            const uint32_t tv = padw ^ (flip << (8u * ((wt >> (2 * j)) & 3u)));
+            tabw[H2 * u + j + 16 * i] = tv; tabw[H2 * u + j + 16 * i + kBandRing] = tv;
+          }
+        }
+      } else {
+        for (int k = u; k < kChunk; k += TP) {
+          const int x = Xc + kChunk + k;
+          const uint32_t tv = table_word(packed_code(aw, x, n), padw, flip);
+          tabw[k] = tv; tabw[k + kBandRing] = tv;
+        }
+      }
+      RA = RN; RN = funnel64(r_last, r_new, wr_sh); r_last = r_new;
+      TC = funnel64(c_last, c_new, wc_sh); c_last = c_new;
       w.sync();
       // ring windows of this thread: selp[h] = selector of row y (read back to -(S/2 - 1)); tabp[h] = table of column x
-      const uint32_t* selp = sel + ((Y0 + c * kChunk - (H2 - 1)) & (kBandRing - 1)) + (H2 - 1);
-      const uint32_t* tabp = tab + ((X0 + c * kChunk) & (kBandRing - 1));
+      const uint32_t* selp = sel + ((c * kChunk - H2 * u - (H2 - 1)) & (kBandRing - 1)) + (H2 - 1);
+      const uint32_t* tabp = tab + ((c * kChunk + H2 * u) & (kBandRing - 1));
       uint32_t a[H2 + 1], b[H2 + 1], sv[H2];        // columns x .. x + S/2 (and 16 further right), rows y .. y - S/2 + 1
 #pragma unroll
       for (int e = 0; e < H2; ++e) { a[e] = tabp[e]; b[e] = tabp[e + 16]; }
@@ -518,5 +577,18 @@ __global__ void __launch_bounds__(64, 6) sw_banded4_kernel(const __grid_constant
 #endif
 
 const void* banded4_kernel(int mode);
+
+#ifdef __CUDACC__
+// Two threads per pair with sixteen register sets each (sixteen pairs per warp, one warp per CTA: the rings of sixteen
+// pairs are 36 KB of shared memory).  Half the shuffles, border PRMTs and ring loads per cell of the layout above.
+template <int MODE>
+__global__ void __launch_bounds__(32, 6) sw_banded2_kernel(const __grid_constant__ BandedParams P) {
+  __shared__ BandedWarpSmemS<16> sm;
+  WarpCtx w{(int)(threadIdx.x & 31)};
+  banded_warpS<MODE, 16>(P, w, (long long)blockIdx.x, (long long)gridDim.x, &sm);
+}
+#endif
+
+const void* banded2_kernel(int mode);
 
 }  // namespace swb

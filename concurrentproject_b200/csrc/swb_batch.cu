@@ -29,6 +29,9 @@ const void* banded_kernel(int mode) {
 const void* banded4_kernel(int mode) {
   return mode == 0 ? (const void*)sw_banded4_kernel<0> : (const void*)sw_banded4_kernel<1>;
 }
+const void* banded2_kernel(int mode) {
+  return mode == 0 ? (const void*)sw_banded2_kernel<0> : (const void*)sw_banded2_kernel<1>;
+}
 const void* banded8_kernel(int mode) {
   return mode == 0 ? (const void*)sw_banded8_kernel<0> : (const void*)sw_banded8_kernel<1>;
 }

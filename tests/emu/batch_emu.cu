@@ -51,6 +51,12 @@ static void run_banded4_lane(const BandedParams* P, WarpShared* ws, int lane, lo
   banded_warpS<MODE, 8>(*P, w, wid, nw, sm);
 }
 
+template <int MODE>
+static void run_banded2_lane(const BandedParams* P, WarpShared* ws, int lane, long long wid, long long nw, BandedWarpSmemS<16>* sm) {
+  WarpCtx w{lane, ws};
+  banded_warpS<MODE, 16>(*P, w, wid, nw, sm);
+}
+
 int main(int argc, char** argv) {
   if (argc < 6) { fprintf(stderr, "usage: batch_emu pairs.bin batch|banded R MODE G [ma mi gi ge [band_lo]]\n"); return 2; }
   FILE* f = fopen(argv[1], "rb");
@@ -97,6 +103,11 @@ int main(int argc, char** argv) {
     if (G == 16) {                                     // the 16-threads-per-pair layout
       std::vector<BandedWarpSmem> sm(W);
       auto fn = mode ? run_banded_lane<1> : run_banded_lane<0>;
+      for (int w = 0; w < W; ++w) for (int l = 0; l < 32; ++l) th.emplace_back(fn, &P, &ws[w], l, (long long)w, (long long)W, &sm[w]);
+      for (auto& x : th) x.join();
+    } else if (G == 2) {                               // two threads per pair, sixteen register sets each
+      std::vector<BandedWarpSmemS<16>> sm(W);
+      auto fn = mode ? run_banded2_lane<1> : run_banded2_lane<0>;
       for (int w = 0; w < W; ++w) for (int l = 0; l < 32; ++l) th.emplace_back(fn, &P, &ws[w], l, (long long)w, (long long)W, &sm[w]);
       for (auto& x : th) x.join();
     } else if (G == 4) {                               // four threads per pair, eight register sets each

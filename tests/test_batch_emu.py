@@ -59,11 +59,11 @@ def test_batch_kernel_body(emu, R, G, max_read):
         assert emu(s1, s2, "batch", R, mode, G, p) == O.gotoh_batch(s1, s2, p).tolist(), (R, G, p, mode)
 
 
-@pytest.mark.parametrize("G", [16, 8, 4])
+@pytest.mark.parametrize("G", [16, 8, 4, 2])
 def test_banded_kernel_body(emu, G):
-    """The three layouts of the banded kernel: 16 threads per pair with two register sets, 8 threads with four, 4 with eight."""
+    """The four layouts of the banded kernel: 16 threads per pair with two register sets, 8 with four, 4 with eight, 2 with sixteen."""
     r = np.random.default_rng(9)
-    a = [bytes(rng.random_acgt(60, k, int(r.integers(1, 420)))) for k in range(11 if G == 4 else 7)]
+    a = [bytes(rng.random_acgt(60, k, int(r.integers(1, 420)))) for k in range({4: 11, 2: 19}.get(G, 7))]
     b = [bytes(rng.mutate(np.frombuffer(x, np.uint8), 60, 100 + k, 0.08, 0.03)) if k % 3 else bytes(rng.random_acgt(61, k, 300))
          for k, x in enumerate(a)]
     for lo in (-32, -5, 0, -60, 17):

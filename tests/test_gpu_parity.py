@@ -361,7 +361,7 @@ def _long_read_pairs(seed, npairs, n):
     return s1, s2
 
 
-@pytest.mark.parametrize("config", [0, 8, 16])
+@pytest.mark.parametrize("config", [0, 2, 8, 16])
 @pytest.mark.parametrize("no_linear", [False, True])
 def test_banded_batch_against_oracle(api, no_linear, config):
     s1, s2 = _long_read_pairs(800, 24, 3000)
