@@ -500,15 +500,21 @@ def batch_record(env, args, name, steps, warmup):
         raise SystemExit("bench.py: host batch call disagrees with the device-resident pass")
     # the same call with the host batch already in the resident 2-bit format (a quarter of the PCIe bytes, no pack kernel)
     e2e_packed_s, np_pk = 0.0, 0
-    if not banded and ne:
+    if ne:
         np_pk = min(ne, 1000000)
-        qw, qs, tw, ts, ql, tl = api.pack_batch_host(r_e[:np_pk * l1], o1[:np_pk], ln1[:np_pk], w_e[:np_pk * l2], o2[:np_pk], ln2[:np_pk])
         pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
-        qw, tw, ql, tl = pin(qw), pin(tw), pin(ql), pin(tl)
-        api.score_batch_packed(qw, qs, tw, ts, ql, tl)
+        if banded:
+            w1, st1, w2, st2 = api.pack_banded_host(r_e[:np_pk * l1], o1[:np_pk], ln1[:np_pk], w_e[:np_pk * l2], o2[:np_pk], ln2[:np_pk])
+            w1, w2 = pin(w1), pin(w2)
+            packed_call = lambda: api.score_banded_batch_packed(w1, st1, w2, st2, ln1[:np_pk], ln2[:np_pk], lo, hi)
+        else:
+            qw, qs, tw, ts, ql, tl = api.pack_batch_host(r_e[:np_pk * l1], o1[:np_pk], ln1[:np_pk], w_e[:np_pk * l2], o2[:np_pk], ln2[:np_pk])
+            qw, tw, ql, tl = pin(qw), pin(tw), pin(ql), pin(tl)
+            packed_call = lambda: api.score_batch_packed(qw, qs, tw, ts, ql, tl)
+        packed_call()
         env.barrier()
         t1 = time.perf_counter()
-        outp = api.score_batch_packed(qw, qs, tw, ts, ql, tl)
+        outp = packed_call()
         e2e_packed_s = time.perf_counter() - t1
         if outp.tolist() != out[:np_pk].tolist():
             raise SystemExit("bench.py: packed host batch call disagrees with the byte call")
@@ -556,8 +562,8 @@ def batch_record(env, args, name, steps, warmup):
                     "call": f"swb200_score{'_banded' if banded else ''}_batch(pinned host bytes) on {ne} pairs per GPU ({ne_total} in all), wall clock, max over ranks"},
             "e2e_packed": None if not np_pk_total else {
                 "value": round(float(np_pk_total) * per_pair / (e2e_packed_ms * 1e-3) / 1e9, 1), "unit": "GCUPS",
-                "h2d_bytes_per_step": int(np_pk * ((l1 + 31) // 32 + (l2 + 31) // 32 + 2) * 8 + np_pk * 8) * env.world, "d2h_bytes_per_step": int(4 * np_pk) * env.world,
-                "call": f"swb200_score_batch_packed(pinned host words, 2 bits per base) on {np_pk} pairs per GPU, wall clock, max over ranks"},
+                "h2d_bytes_per_step": int(np_pk * ((l1 + 31) // 32 + (l2 + 31) // 32 + (4 if banded else 2)) * 8 + np_pk * 8) * env.world, "d2h_bytes_per_step": int(4 * np_pk) * env.world,
+                "call": f"swb200_score{'_banded' if banded else ''}_batch_packed(pinned host words, 2 bits per base) on {np_pk} pairs per GPU, wall clock, max over ranks"},
             "roofline": {"bound": "int_alu", "achieved": round(value, 1), "peak": round(peak, 1), "unit": "GCUPS",
                          "frac": round(value / peak, 4), "traffic": None,
                          "note": f"batch kernel on {env.world} GPU(s); peak = {env.world} x 148 SM x {f_mhz} MHz x L=64 x V=2 / 7"},

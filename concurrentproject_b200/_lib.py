@@ -74,6 +74,12 @@ EXPORTS = {
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "swb200_score_batch_packed": ([C.POINTER(C.c_ulonglong), C.c_longlong, C.POINTER(C.c_ulonglong), C.c_longlong, C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.c_longlong, C.POINTER(Params), C.POINTER(Options), C.POINTER(C.c_int)], C.c_int),
+    "swb200_banded_strides": ([C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)], C.c_int),
+    "swb200_pack_banded_host": ([U8P, C.POINTER(C.c_longlong), C.POINTER(C.c_int), U8P, C.POINTER(C.c_longlong), C.POINTER(C.c_int),
+                                 C.c_longlong, C.c_longlong, C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)], C.c_int),
+    "swb200_score_banded_batch_packed": ([C.POINTER(C.c_ulonglong), C.c_longlong, C.POINTER(C.c_ulonglong), C.c_longlong, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int), C.c_longlong, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(Options),
+                                          C.POINTER(C.c_int)], C.c_int),
     "swb200_batch_pack_device": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
     "swb200_batch_score": ([C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_void_p], C.c_int),

@@ -389,3 +389,37 @@ def score_batch_packed(qw: np.ndarray, q_stride: int, tw: np.ndarray, t_stride: 
     if rc != 0:
         raise SwbError(rc, "swb200_score_batch_packed")
     return out
+
+
+def pack_banded_host(flat1, off1, len1, flat2, off2, len2):
+    """Raw A,C,G,T bytes -> the resident 2-bit layout for banded scoring (swb200_pack_banded_host; seq1 = columns and
+    seq2 = rows keep their roles): (words1, stride1, words2, stride2)."""
+    n = len(len1)
+    s1, s2 = C.c_longlong(0), C.c_longlong(0)
+    rc = _lib.load().swb200_banded_strides(int(len1.max()) if n else 0, int(len2.max()) if n else 0, C.byref(s1), C.byref(s2))
+    if rc != 0:
+        raise SwbError(rc, "swb200_banded_strides")
+    w1, w2 = np.zeros(max(n, 1) * s1.value, dtype=np.uint64), np.zeros(max(n, 1) * s2.value, dtype=np.uint64)
+    LL, I, U = C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)
+    rc = _lib.load().swb200_pack_banded_host(_ptr(flat1), off1.ctypes.data_as(LL), len1.ctypes.data_as(I), _ptr(flat2),
+                                             off2.ctypes.data_as(LL), len2.ctypes.data_as(I), n, s1.value, s2.value,
+                                             w1.ctypes.data_as(U), w2.ctypes.data_as(U))
+    if rc != 0:
+        raise SwbError(rc, "swb200_pack_banded_host")
+    return w1, s1.value, w2, s2.value
+
+
+def score_banded_batch_packed(w1: np.ndarray, stride1: int, w2: np.ndarray, stride2: int, len1: np.ndarray, len2: np.ndarray,
+                              band_lo: int = -32, band_hi: int = 31, params: Sequence[int] = DEFAULT_PARAMS, *,
+                              no_linear: bool = False) -> np.ndarray:
+    """swb200_score_banded_batch_packed: banded scores of HOST batches already in the 2-bit format (a quarter of the PCIe bytes)."""
+    n = len(len1)
+    out = np.zeros(n, dtype=np.int32)
+    p, o = _params(params), _options(no_linear=no_linear)
+    I, U = C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)
+    rc = _lib.load().swb200_score_banded_batch_packed(w1.ctypes.data_as(U), stride1, w2.ctypes.data_as(U), stride2,
+                                                      len1.ctypes.data_as(I), len2.ctypes.data_as(I), n, band_lo, band_hi,
+                                                      C.byref(p), C.byref(o), out.ctypes.data_as(I))
+    if rc != 0:
+        raise SwbError(rc, "swb200_score_banded_batch_packed")
+    return out

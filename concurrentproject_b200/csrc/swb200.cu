@@ -1990,7 +1990,7 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
 static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_words, long long q_stride,
                                   const unsigned long long* t_words, long long t_stride, const int* q_len, const int* t_len,
                                   long long npairs, int max_short, int max_long, const swb200_params* p, const swb200_options* opt,
-                                  int* scores_out) {
+                                  int* scores_out, int banded = 0, int band_lo = 0, int band_hi = 0) {
   if (npairs == 0) return SWB200_OK;
   const swb200_params pv = p ? *p : swb200_params{1, -1, 1, 1};
   const swb200_options ov = opt ? *opt : swb200_options{};
@@ -2005,7 +2005,7 @@ static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_wor
       (rc = grow(c->hb_tw, c->hb_tw_cap, np * t_stride, false, sc)) || (rc = grow(c->hb_ql, c->hb_ql_cap, np, false, sc)) ||
       (rc = grow(c->hb_tl, c->hb_tl_cap, np, false, sc))) return rc;
   const BatchView all{c->hb_qw, c->hb_tw, c->hb_ql, c->hb_tl, q_stride, t_stride, npairs, max_short, max_long};
-  if ((rc = check_batch_score(all, pv, 0))) return rc;
+  if ((rc = banded ? check_banded_score(all, pv, 1, band_lo, band_hi) : check_batch_score(all, pv, 0))) return rc;
   const long long forced = settings().batch_chunk_bytes;
   const long long target = forced > 0 ? forced : 48LL << 20;
   const long long per_pair = (q_stride + t_stride) * 8 + 8;
@@ -2029,7 +2029,9 @@ static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_wor
     SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
     if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
     const BatchView v{c->hb_qw + k0 * q_stride, c->hb_tw + k0 * t_stride, c->hb_ql + k0, c->hb_tl + k0, q_stride, t_stride, nk, max_short, max_long};
-    if ((rc = launch_batch_score(c, v, pv, ov, sk, c->hb_scores + k0, &c->info))) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
+    rc = banded ? launch_banded_score(c, v, band_lo, pv, ov, sk, c->hb_scores + k0, &c->info)
+                : launch_batch_score(c, v, pv, ov, sk, c->hb_scores + k0, &c->info);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
   }
   SWB_CUDA(cudaEventRecord(c->ev1, sk));
   SWB_CUDA(cudaMemcpyAsync(scores_out, c->hb_scores, npairs * sizeof(int), cudaMemcpyDeviceToHost, sk));
@@ -2052,17 +2054,18 @@ int swb200_batch_strides(int max_short, int max_long, long long* q_stride, long 
 
 // Format conversion on the host (no scoring here): raw A,C,G,T bytes -> the resident 2-bit layout, shorter sequence of
 // each pair first.  Same words as the device packer (swb_batch.cu: pack_batch_kernel) produces.
-int swb200_pack_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
-                           const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
-                           unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len) {
+static int pack_host_impl(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                          const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
+                          unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len, bool keep_order) {
   if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !q_words || !t_words || !q_len || !t_len)))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   for (long long k = 0; k < npairs; ++k) {
-    const bool swap = len1[k] > len2[k];
+    const bool swap = !keep_order && len1[k] > len2[k];
     const unsigned char* q = swap ? seq2_all + off2[k] : seq1_all + off1[k];
     const unsigned char* t = swap ? seq1_all + off1[k] : seq2_all + off2[k];
     const int lq = swap ? len2[k] : len1[k], lt = swap ? len1[k] : len2[k];
-    if (lq < 0 || (lq + 31) / 32 > q_stride || (lt + 31) / 32 + 2 > t_stride) return fail(SWB200_ERR_ARG, "pair longer than the strides allow");
+    if (lq < 0 || lt < 0 || (lq + 31) / 32 + (keep_order ? 2 : 0) > q_stride || (lt + 31) / 32 + 2 > t_stride)
+      return fail(SWB200_ERR_ARG, "pair longer than the strides allow");
     for (int side = 0; side < 2; ++side) {
       const unsigned char* src = side ? t : q;
       const int len = side ? lt : lq;
@@ -2081,6 +2084,65 @@ int swb200_pack_batch_host(const unsigned char* seq1_all, const long long* off1,
     q_len[k] = lq; t_len[k] = lt;
   }
   return SWB200_OK;
+}
+
+int swb200_pack_batch_host(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                           const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
+                           unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len) {
+  return pack_host_impl(seq1_all, off1, len1, seq2_all, off2, len2, npairs, q_stride, t_stride, q_words, t_words, q_len, t_len, false);
+}
+
+// ---- banded batches in the resident format: seq1 (columns) and seq2 (rows) keep their roles ----
+int swb200_banded_strides(int max_len1, int max_len2, long long* stride1, long long* stride2) {
+  if (max_len1 < 0 || max_len2 < 0 || !stride1 || !stride2) return fail(SWB200_ERR_ARG, "bad batch shape");
+  *stride1 = std::max(1, (max_len1 + 31) / 32) + 2;
+  *stride2 = std::max(1, (max_len2 + 31) / 32) + 2;
+  return SWB200_OK;
+}
+
+int swb200_pack_banded_host(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                            const long long* off2, const int* len2, long long npairs, long long stride1, long long stride2,
+                            unsigned long long* words1, unsigned long long* words2) {
+  if (npairs < 0) return fail(SWB200_ERR_ARG, "bad batch arguments");
+  std::vector<int> l1((size_t)std::max<long long>(npairs, 1)), l2((size_t)std::max<long long>(npairs, 1));
+  return pack_host_impl(seq1_all, off1, len1, seq2_all, off2, len2, npairs, stride1, stride2, words1, words2, l1.data(), l2.data(), true);
+}
+
+int swb200_score_banded_batch_packed(const unsigned long long* words1, long long stride1, const unsigned long long* words2,
+                                     long long stride2, const int* len1, const int* len2, long long npairs, int band_lo,
+                                     int band_hi, const swb200_params* p, const swb200_options* opt, int* scores_out) {
+  if (npairs < 0 || stride1 < 3 || stride2 < 3 || (npairs > 0 && (!words1 || !words2 || !len1 || !len2 || !scores_out)))
+    return fail(SWB200_ERR_ARG, "bad batch arguments");
+  if (npairs == 0) return SWB200_OK;
+  int max1 = 0, max2 = 0;
+  for (long long k = 0; k < npairs; ++k) {
+    if (len1[k] < 0 || len2[k] < 0 || (len1[k] + 31) / 32 + 2 > stride1 || (len2[k] + 31) / 32 + 2 > stride2)
+      return fail(SWB200_ERR_ARG, "pair lengths do not fit the strides");
+    max1 = std::max(max1, len1[k]); max2 = std::max(max2, len2[k]);
+  }
+  {
+    std::unique_lock<std::mutex> pl(g_pool.mu);
+    const int G = (int)g_pool.ctx.size();
+    if (G > 1 && npairs >= 2LL * G) {
+      const long long per = (npairs + G - 1) / G;
+      int rc = pool_parallel(G, [&](int g) -> int {
+        const long long k0 = std::min<long long>(npairs, (long long)g * per), k1 = std::min<long long>(npairs, k0 + per);
+        return score_batch_packed_ctx(g_pool.ctx[(size_t)g], words1 + k0 * stride1, stride1, words2 + k0 * stride2, stride2, len1 + k0,
+                                      len2 + k0, k1 - k0, max1, max2, p, opt, scores_out + k0, 1, band_lo, band_hi);
+      });
+      if (rc) return rc;
+      g_pool.info = g_pool.ctx[0]->info;
+      g_pool.info.cells = 0; g_pool.info.engine_ms = 0;
+      for (int g = 0; g < G; ++g) { g_pool.info.cells += g_pool.ctx[(size_t)g]->info.cells; g_pool.info.engine_ms = std::max(g_pool.info.engine_ms, g_pool.ctx[(size_t)g]->info.engine_ms); }
+      g_pool.info_valid = true;
+      return SWB200_OK;
+    }
+    g_pool.info_valid = false;
+  }
+  swb200_ctx* c = nullptr;
+  int rc = default_ctx(&c);
+  if (rc) return rc;
+  return score_batch_packed_ctx(c, words1, stride1, words2, stride2, len1, len2, npairs, max1, max2, p, opt, scores_out, 1, band_lo, band_hi);
 }
 
 int swb200_score_batch_packed(const unsigned long long* q_words, long long q_stride, const unsigned long long* t_words,

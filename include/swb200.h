@@ -199,6 +199,19 @@ SWB200_API int swb200_score_batch_packed(const unsigned long long* q_words, long
                                          const int* t_len, long long npairs, const swb200_params* p,
                                          const swb200_options* opt, int* scores_out);
 
+/* Banded batches (swb200_score_banded_batch below) from HOST words in the same 2-bit format.  seq1 (columns) and seq2
+ * (rows) keep their roles: stride1 words of seq1 and stride2 words of seq2 per pair (swb200_banded_strides), len1 / len2
+ * as given by the caller.  swb200_pack_banded_host is the format conversion on the host. */
+SWB200_API int swb200_banded_strides(int max_len1, int max_len2, long long* stride1, long long* stride2);
+SWB200_API int swb200_pack_banded_host(const unsigned char* seq1_all, const long long* off1, const int* len1,
+                                       const unsigned char* seq2_all, const long long* off2, const int* len2,
+                                       long long npairs, long long stride1, long long stride2,
+                                       unsigned long long* words1, unsigned long long* words2);
+SWB200_API int swb200_score_banded_batch_packed(const unsigned long long* words1, long long stride1,
+                                                const unsigned long long* words2, long long stride2, const int* len1,
+                                                const int* len2, long long npairs, int band_lo, int band_hi,
+                                                const swb200_params* p, const swb200_options* opt, int* scores_out);
+
 /* Device-resident form: pack once (2-bit codes in HBM, the resident format), score many times.
  * All pointers are DEVICE pointers; max_short / max_long bound min(len1,len2) / max(len1,len2) over the
  * batch; total_cells (sum of len1*len2) is only recorded for swb200_last_run.  d_scores: npairs ints.

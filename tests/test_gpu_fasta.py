@@ -110,3 +110,30 @@ def test_packed_host_batches():
     with pytest.raises(api.SwbError):
         api.pack_batch_host(np.frombuffer(b"ACGN", dtype=np.uint8), np.zeros(1, np.int64), np.array([4], np.int32),
                             np.frombuffer(b"ACGT", dtype=np.uint8), np.zeros(1, np.int64), np.array([4], np.int32))
+
+
+def test_packed_host_banded_batches():
+    """swb200_score_banded_batch_packed: banded scoring of a host batch that arrives in the 2-bit format (seq1 = columns and
+    seq2 = rows keep their roles, either may be the longer one); ragged lengths from empty to 2 500, three bands, two
+    parameter sets, many small chunks."""
+    from concurrentproject_b200 import api
+    r = np.random.default_rng(77)
+    s1, s2 = [], []
+    for k in range(150):
+        a = rng.random_acgt(77, k, int(r.integers(0, 2500)))
+        b = rng.mutate(a, 77, 1000 + k, 0.08, 0.02) if k % 3 else rng.random_acgt(77, 2000 + k, int(r.integers(0, 2500)))
+        s1.append(bytes(a)); s2.append(bytes(b))
+    f1, o1, l1 = api._flatten(s1); f2, o2, l2 = api._flatten(s2)
+    w1, st1, w2, st2 = api.pack_banded_host(f1, o1, l1, f2, o2, l2)
+    for lo in (-32, 0, -63):
+        for p in (O.DEFAULT, (2, -3, 5, 1)):
+            want = O.gotoh_banded_batch(s1, s2, lo, lo + 63, p)
+            assert np.array_equal(api.score_banded_batch_packed(w1, st1, w2, st2, l1, l2, lo, lo + 63, p), want), (lo, p)
+    assert np.array_equal(api.score_banded_batch_packed(w1, st1, w2, st2, l1, l2), api.score_banded_batch(s1, s2))
+    api.configure("batch_chunk_bytes", "30000")
+    try:
+        assert np.array_equal(api.score_banded_batch_packed(w1, st1, w2, st2, l1, l2), O.gotoh_banded_batch(s1, s2, -32, 31))
+    finally:
+        api.configure("batch_chunk_bytes", "0")
+    with pytest.raises(api.SwbError):
+        api.score_banded_batch_packed(w1, st1, w2, st2, l1, l2, -10, 10)
