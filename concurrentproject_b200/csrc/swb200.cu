@@ -1399,18 +1399,34 @@ static int check_banded_score(const BatchView& v, const swb200_params& p, int ke
   return SWB200_OK;
 }
 
+// kernel, threads per CTA and pairs per CTA of the banded layout the options ask for
+static const void* banded_layout(const swb200_params& p, const swb200_options& o, int* threads, int* mode_out) {
+  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
+  const bool wide = o.config == 16, mid = o.config == 8, two = o.config == 2;
+  *threads = wide ? 256 : (mid ? 128 : (two ? 32 : 64));
+  if (mode_out) *mode_out = mode;
+  return wide ? swb::banded_kernel(mode) : (mid ? swb::banded8_kernel(mode) : (two ? swb::banded2_kernel(mode) : swb::banded4_kernel(mode)));
+}
+
+// pairs one full wave of resident CTAs scores (16 pairs per CTA in every layout)
+static long long banded_wave_pairs(swb200_ctx* c, const swb200_params& p, const swb200_options& o) {
+  int threads = 0;
+  const void* kern = banded_layout(p, o, &threads, nullptr);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return 16LL * c->sms * per_sm;
+}
+
 static int launch_banded_score(swb200_ctx* c, const BatchView& v, int band_lo, const swb200_params& p,
                                const swb200_options& o, cudaStream_t s, int* d_scores, swb200_run_info* info) {
   if (v.npairs == 0) return SWB200_OK;
-  const int mode = (p.gap_init == p.gap_ext && !o.no_linear) ? 1 : 0;
-  // two layouts: 8 threads per pair with four register sets each (round 2: half the shuffles per cell; the default) and
-  // 16 threads per pair with two (options.config = 16, kept for comparison)
-  // three layouts: 4 threads per pair with eight register sets each (the default: fewest shuffles and loads per cell),
-  // 8 threads with four (options.config = 8) and 16 threads with two (options.config = 16), both kept for comparison
-  // (options.config = 2: two threads with sixteen sets)
+  // four layouts: 4 threads per pair with eight register sets each (the default), 8 threads with four (options.config =
+  // 8), 16 threads with two (16) and 2 threads with sixteen (2), the last three kept for comparison
   const bool wide = o.config == 16, mid = o.config == 8, two = o.config == 2;
-  const void* kern = wide ? swb::banded_kernel(mode) : (mid ? swb::banded8_kernel(mode) : (two ? swb::banded2_kernel(mode) : swb::banded4_kernel(mode)));
-  const int threads = wide ? 256 : (mid ? 128 : (two ? 32 : 64)), pairs_per_cta = 16;
+  int threads = 0, mode = 0;
+  const void* kern = banded_layout(p, o, &threads, &mode);
+  const int pairs_per_cta = 16;
   // several CTAs of 34-35 KB static shared memory per SM: ask for the large shared-memory carve-out
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   swb::BandedParams P{};
@@ -2009,7 +2025,13 @@ static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_wor
   const long long forced = settings().batch_chunk_bytes;
   const long long target = forced > 0 ? forced : 48LL << 20;
   const long long per_pair = (q_stride + t_stride) * 8 + 8;
-  const long long chunk_pairs = std::max<long long>(forced > 0 ? 1 : 1024, target / per_pair);
+  long long chunk_pairs = std::max<long long>(forced > 0 ? 1 : 1024, target / per_pair);
+  if (banded && forced <= 0) {
+    // a banded kernel runs as long as its pairs are long however few they are: chunks are whole waves of resident CTAs
+    // (10 kb reads: 14 208 pairs = 72 MB; 48 MB chunks left a third of every launch idle: 42.5 -> 30 ms for 250 000 pairs)
+    const long long wave = banded_wave_pairs(c, pv, ov);
+    chunk_pairs = wave * std::max<long long>(1, (target + wave * per_pair / 2) / (wave * per_pair));
+  }
   const size_t nchunks = (size_t)((npairs + chunk_pairs - 1) / chunk_pairs);
   while (c->chunk_events.size() < nchunks + 1) {
     cudaEvent_t e;
