@@ -386,6 +386,28 @@ def test_banded_other_bands_params_and_edges(api):
         api.score_banded_batch(e1, e2, -10, 10)      # only 64-diagonal bands in this kernel
 
 
+def test_banded_every_ring_alignment(api):
+    """The banded kernel refills its rings from rolling 64-bit windows of the packed sequences; the bit offset of those
+    windows follows band_lo.  Every band_lo from -70 to 37 (all 32 row and column offsets, bands that start outside the
+    matrix), ragged lengths up to 1 500 with related and unrelated pairs, both kernels."""
+    r = np.random.default_rng(4242)
+    s1, s2 = [], []
+    for k in range(48):
+        n = int(r.integers(1, 1500)) if k % 6 else int(r.choice([31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129]))
+        a = rng.random_acgt(4242, k, n)
+        if k % 4 == 3:
+            b = rng.random_acgt(4242, 500 + k, int(r.integers(1, 1500)))
+        else:
+            b = rng.mutate(a, 4242, 100 + k, 0.08, 0.03)
+            cut = int(r.integers(0, 40))
+            b = b[cut:] if k % 2 else np.concatenate([rng.random_acgt(4242, 900 + k, cut), b])      # the diagonal starts off-centre
+        s1.append(bytes(a)); s2.append(bytes(b))
+    for lo in range(-70, 38):
+        p, nl = ((O.DEFAULT, False), ((2, -3, 5, 1), True), (O.DEFAULT, True))[lo % 3]
+        want = O.gotoh_banded_batch(s1, s2, lo, lo + 63, p)
+        assert api.score_banded_batch(s1, s2, lo, lo + 63, p, no_linear=nl).tolist() == want.tolist(), (lo, p, nl)
+
+
 @pytest.mark.parametrize("config", [1, 2, 3, 4, 5])
 def test_rebased_16_bit_lanes(api, config):
     """Scores far beyond 32767 in packed 16-bit lanes relative to a moving base: the level climbs (identical
