@@ -1522,18 +1522,24 @@ static int score_batch_host_ctx(swb200_ctx* c, const unsigned char* seq1_all, co
   int rc;
   long long bytes1 = 0, bytes2 = 0, cells = 0, base1 = LLONG_MAX, base2 = LLONG_MAX;
   int max_short = 0, max_long = 0;
-  for (long long k = 0; k < npairs; ++k) {
-    if (len1[k] < 0 || len2[k] < 0 || off1[k] < 0 || off2[k] < 0) return fail(SWB200_ERR_ARG, "negative length or offset");
-    bytes1 = std::max(bytes1, off1[k] + len1[k]);
-    bytes2 = std::max(bytes2, off2[k] + len2[k]);
-    base1 = std::min(base1, off1[k]);
-    base2 = std::min(base2, off2[k]);
-    if (banded) { max_short = std::max(max_short, len1[k]); max_long = std::max(max_long, len2[k]); }
-    else {
-      max_short = std::max(max_short, std::min(len1[k], len2[k]));
-      max_long = std::max(max_long, std::max(len1[k], len2[k]));
+  {
+    // branch-free (this pass runs before the first copy can start: 1 ns per pair instead of 2-3)
+    long long neg = 0;
+    int mx1 = 0, mx2 = 0, mxmin = 0;
+    for (long long k = 0; k < npairs; ++k) {
+      const int a = len1[k], b = len2[k];
+      const long long o1 = off1[k], o2 = off2[k];
+      neg |= (long long)(a | b) | o1 | o2;                       // sign bit set iff any of the four is negative
+      bytes1 = std::max(bytes1, o1 + a);
+      bytes2 = std::max(bytes2, o2 + b);
+      base1 = std::min(base1, o1);
+      base2 = std::min(base2, o2);
+      mx1 = std::max(mx1, a); mx2 = std::max(mx2, b); mxmin = std::max(mxmin, std::min(a, b));
+      cells += (long long)a * b;
     }
-    cells += (long long)len1[k] * len2[k];
+    if (neg < 0) return fail(SWB200_ERR_ARG, "negative length or offset");
+    if (banded) { max_short = mx1; max_long = mx2; }
+    else { max_short = mxmin; max_long = std::max(mx1, mx2); }
   }
   base1 &= ~15LL; base2 &= ~15LL;          // staged bytes keep their position relative to the range's lowest offset
   bytes1 -= base1; bytes2 -= base2;
@@ -1559,9 +1565,44 @@ static int score_batch_host_ctx(swb200_ctx* c, const unsigned char* seq1_all, co
   const BatchView all{c->hb_qw, c->hb_tw, c->hb_ql, c->hb_tl, q_stride, t_stride, npairs, max_short, max_long};
   if ((rc = banded ? check_banded_score(all, pv, 1, band_lo, band_hi) : check_batch_score(all, pv, 0))) return rc;
 
-  // chunk boundaries and the byte range each chunk touches in the two host buffers
+  // A chunk is issued (copies on own_stream, pack + score on aux_stream) the moment the scan over the pairs has found its
+  // end, so the GPU works while the host is still cutting the later chunks.
   struct Chunk { long long k0, k1, lo1, hi1, lo2, hi2; };
-  std::vector<Chunk> chunks;
+  c->info = swb200_run_info{};
+  c->info.cells = cells;
+  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_off1, off1, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_off2, off2, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_len1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
+  SWB_CUDA(cudaMemcpyAsync(c->hb_len2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
+  bool first = true;
+  size_t ci = 0;
+  auto issue = [&](const Chunk& ch) -> int {
+    while (c->chunk_events.size() < ci + 1) {
+      cudaEvent_t e;
+      SWB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->chunk_events.push_back(e);
+    }
+    if (ch.hi1 > ch.lo1) SWB_CUDA(cudaMemcpyAsync(c->hb_seq1 + (ch.lo1 - base1), seq1_all + ch.lo1, (size_t)(ch.hi1 - ch.lo1), cudaMemcpyHostToDevice, sc));
+    if (ch.hi2 > ch.lo2) SWB_CUDA(cudaMemcpyAsync(c->hb_seq2 + (ch.lo2 - base2), seq2_all + ch.lo2, (size_t)(ch.hi2 - ch.lo2), cudaMemcpyHostToDevice, sc));
+    SWB_CUDA(cudaEventRecord(c->chunk_events[ci], sc));
+    SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
+    ci += 1;
+    if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
+    const long long nk = ch.k1 - ch.k0;
+    const long long total = nk * (q_stride + t_stride);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);
+    // the pack kernel adds the absolute offsets: hand it the staging pointers shifted back by the range's base
+    swb::launch_pack_batch(c->hb_seq1 - base1, c->hb_off1 + ch.k0, c->hb_len1 + ch.k0, c->hb_seq2 - base2, c->hb_off2 + ch.k0, c->hb_len2 + ch.k0, nk,
+                           q_stride, t_stride, c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0,
+                           c->hb_tl + ch.k0, banded ? 1 : 0, c->d_result, blocks, sk);
+    SWB_CUDA(cudaGetLastError());
+    c->info.aux_launches += 1;
+    const BatchView v{c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0, c->hb_tl + ch.k0,
+                      q_stride, t_stride, nk, max_short, max_long};
+    return banded ? launch_banded_score(c, v, band_lo, pv, ov, sk, c->hb_scores + ch.k0, &c->info)
+                  : launch_batch_score(c, v, pv, ov, sk, c->hb_scores + ch.k0, &c->info);
+  };
   {
     const long long forced = settings().batch_chunk_bytes;
     const bool ov_chunk = forced > 0;                                // tests: force many small chunks
@@ -1575,46 +1616,11 @@ static int score_batch_host_ctx(swb200_ctx* c, const unsigned char* seq1_all, co
       acc += (long long)len1[k] + len2[k];
       if ((acc >= target && k + 1 - cur.k0 >= min_pairs) || k + 1 == npairs) {
         cur.k1 = k + 1;
-        chunks.push_back(cur);
+        if ((rc = issue(cur))) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
         cur = Chunk{k + 1, 0, LLONG_MAX, 0, LLONG_MAX, 0};
         acc = 0;
       }
     }
-  }
-  while (c->chunk_events.size() < chunks.size() + 1) {
-    cudaEvent_t e;
-    SWB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->chunk_events.push_back(e);
-  }
-  c->info = swb200_run_info{};
-  c->info.cells = cells;
-  SWB_CUDA(cudaMemsetAsync(c->d_result, 0, 10 * sizeof(int), sc));
-  SWB_CUDA(cudaMemcpyAsync(c->hb_off1, off1, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
-  SWB_CUDA(cudaMemcpyAsync(c->hb_off2, off2, npairs * sizeof(long long), cudaMemcpyHostToDevice, sc));
-  SWB_CUDA(cudaMemcpyAsync(c->hb_len1, len1, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
-  SWB_CUDA(cudaMemcpyAsync(c->hb_len2, len2, npairs * sizeof(int), cudaMemcpyHostToDevice, sc));
-  bool first = true;
-  for (size_t ci = 0; ci < chunks.size(); ++ci) {
-    const Chunk& ch = chunks[ci];
-    if (ch.hi1 > ch.lo1) SWB_CUDA(cudaMemcpyAsync(c->hb_seq1 + (ch.lo1 - base1), seq1_all + ch.lo1, (size_t)(ch.hi1 - ch.lo1), cudaMemcpyHostToDevice, sc));
-    if (ch.hi2 > ch.lo2) SWB_CUDA(cudaMemcpyAsync(c->hb_seq2 + (ch.lo2 - base2), seq2_all + ch.lo2, (size_t)(ch.hi2 - ch.lo2), cudaMemcpyHostToDevice, sc));
-    SWB_CUDA(cudaEventRecord(c->chunk_events[ci], sc));
-    SWB_CUDA(cudaStreamWaitEvent(sk, c->chunk_events[ci], 0));
-    if (first) { SWB_CUDA(cudaEventRecord(c->ev0, sk)); first = false; }
-    const long long nk = ch.k1 - ch.k0;
-    const long long total = nk * (q_stride + t_stride);
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 64LL * c->sms);
-    // the pack kernel adds the absolute offsets: hand it the staging pointers shifted back by the range's base
-    swb::launch_pack_batch(c->hb_seq1 - base1, c->hb_off1 + ch.k0, c->hb_len1 + ch.k0, c->hb_seq2 - base2, c->hb_off2 + ch.k0, c->hb_len2 + ch.k0, nk,
-                           q_stride, t_stride, c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0,
-                           c->hb_tl + ch.k0, banded ? 1 : 0, c->d_result, blocks, sk);
-    SWB_CUDA(cudaGetLastError());
-    c->info.aux_launches += 1;
-    const BatchView v{c->hb_qw + ch.k0 * q_stride, c->hb_tw + ch.k0 * t_stride, c->hb_ql + ch.k0, c->hb_tl + ch.k0,
-                      q_stride, t_stride, nk, max_short, max_long};
-    rc = banded ? launch_banded_score(c, v, band_lo, pv, ov, sk, c->hb_scores + ch.k0, &c->info)
-                : launch_batch_score(c, v, pv, ov, sk, c->hb_scores + ch.k0, &c->info);
-    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sk); return rc; }
   }
   SWB_CUDA(cudaEventRecord(c->ev1, sk));
   SWB_CUDA(cudaMemcpyAsync(scores_out, c->hb_scores, npairs * sizeof(int), cudaMemcpyDeviceToHost, sk));
@@ -2003,10 +2009,28 @@ static int score_batch_host(const unsigned char* seq1_all, const long long* off1
 }
 
 // ---- host batches that are ALREADY in the resident 2-bit format: a quarter of the bytes over PCIe, no pack kernel ----
+// One branch-free pass over the lengths of a packed host batch (a loop with early returns cost 1-2 ns per pair, 2-4 ms
+// per million pairs BEFORE the first copy started): maxima, sum of cells, and whether any pair breaks the rules.
+struct LenScan { int max_q = 0, max_t = 0; long long cells = 0; bool bad = false; };
+static LenScan scan_lens(const int* q_len, const int* t_len, long long k0, long long k1, bool ordered) {
+  LenScan r;
+  int bad = 0;
+  for (long long k = k0; k < k1; ++k) {
+    const int q = q_len[k], t = t_len[k];
+    bad |= (q | t) < 0;
+    bad |= ordered & (t < q);
+    r.max_q = q > r.max_q ? q : r.max_q;
+    r.max_t = t > r.max_t ? t : r.max_t;
+    r.cells += (long long)q * t;
+  }
+  r.bad = bad != 0;
+  return r;
+}
+
 static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_words, long long q_stride,
                                   const unsigned long long* t_words, long long t_stride, const int* q_len, const int* t_len,
                                   long long npairs, int max_short, int max_long, const swb200_params* p, const swb200_options* opt,
-                                  int* scores_out, int banded = 0, int band_lo = 0, int band_hi = 0) {
+                                  int* scores_out, int banded = 0, int band_lo = 0, int band_hi = 0, long long cells_known = -1) {
   if (npairs == 0) return SWB200_OK;
   const swb200_params pv = p ? *p : swb200_params{1, -1, 1, 1};
   const swb200_options ov = opt ? *opt : swb200_options{};
@@ -2023,7 +2047,7 @@ static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_wor
   const BatchView all{c->hb_qw, c->hb_tw, c->hb_ql, c->hb_tl, q_stride, t_stride, npairs, max_short, max_long};
   if ((rc = banded ? check_banded_score(all, pv, 1, band_lo, band_hi) : check_batch_score(all, pv, 0))) return rc;
   const long long forced = settings().batch_chunk_bytes;
-  const long long target = forced > 0 ? forced : 48LL << 20;
+  const long long target = forced > 0 ? forced : (banded ? 48LL << 20 : 24LL << 20);   // measured: bench/batch_e2e.py, bench/banded_e2e.py
   const long long per_pair = (q_stride + t_stride) * 8 + 8;
   long long chunk_pairs = std::max<long long>(forced > 0 ? 1 : 1024, target / per_pair);
   if (banded && forced <= 0) {
@@ -2039,7 +2063,8 @@ static int score_batch_packed_ctx(swb200_ctx* c, const unsigned long long* q_wor
     c->chunk_events.push_back(e);
   }
   c->info = swb200_run_info{};
-  for (long long k = 0; k < npairs; ++k) c->info.cells += (long long)q_len[k] * t_len[k];
+  if (cells_known >= 0) c->info.cells = cells_known;
+  else for (long long k = 0; k < npairs; ++k) c->info.cells += (long long)q_len[k] * t_len[k];
   bool first = true;
   for (size_t ci = 0; ci < nchunks; ++ci) {
     const long long k0 = (long long)ci * chunk_pairs, nk = std::min(chunk_pairs, npairs - k0);
@@ -2173,21 +2198,31 @@ int swb200_score_batch_packed(const unsigned long long* q_words, long long q_str
   if (npairs < 0 || q_stride < 1 || t_stride < 3 || (npairs > 0 && (!q_words || !t_words || !q_len || !t_len || !scores_out)))
     return fail(SWB200_ERR_ARG, "bad batch arguments");
   if (npairs == 0) return SWB200_OK;
-  int max_short = 0, max_long = 0;
-  for (long long k = 0; k < npairs; ++k) {
-    if (q_len[k] < 0 || t_len[k] < q_len[k] || (q_len[k] + 31) / 32 > q_stride || (t_len[k] + 31) / 32 + 2 > t_stride)
-      return fail(SWB200_ERR_ARG, "pair lengths do not fit the strides (q must be the shorter sequence)");
-    max_short = std::max(max_short, q_len[k]); max_long = std::max(max_long, t_len[k]);
-  }
+  auto lens_ok = [&](const LenScan& sc) {
+    return !sc.bad && (sc.max_q + 31) / 32 <= q_stride && (sc.max_t + 31) / 32 + 2 <= t_stride;
+  };
+  const char* const lens_msg = "pair lengths do not fit the strides (q must be the shorter sequence)";
   {
     std::unique_lock<std::mutex> pl(g_pool.mu);
     const int G = (int)g_pool.ctx.size();
     if (G > 1 && npairs >= 2LL * G) {
       const long long per = (npairs + G - 1) / G;
-      int rc = pool_parallel(G, [&](int g) -> int {
+      std::vector<LenScan> scans((size_t)G);
+      int rc = pool_parallel(G, [&](int g) -> int {                      // every shard's lengths scanned by its own thread
+        const long long k0 = std::min<long long>(npairs, (long long)g * per), k1 = std::min<long long>(npairs, k0 + per);
+        scans[(size_t)g] = scan_lens(q_len, t_len, k0, k1, true);
+        return SWB200_OK;
+      });
+      if (rc) return rc;
+      int max_short = 0, max_long = 0;
+      for (const LenScan& sc : scans) {
+        if (!lens_ok(sc)) return fail(SWB200_ERR_ARG, lens_msg);
+        max_short = std::max(max_short, sc.max_q); max_long = std::max(max_long, sc.max_t);
+      }
+      rc = pool_parallel(G, [&](int g) -> int {
         const long long k0 = std::min<long long>(npairs, (long long)g * per), k1 = std::min<long long>(npairs, k0 + per);
         return score_batch_packed_ctx(g_pool.ctx[(size_t)g], q_words + k0 * q_stride, q_stride, t_words + k0 * t_stride, t_stride, q_len + k0,
-                                      t_len + k0, k1 - k0, max_short, max_long, p, opt, scores_out + k0);
+                                      t_len + k0, k1 - k0, max_short, max_long, p, opt, scores_out + k0, 0, 0, 0, scans[(size_t)g].cells);
       });
       if (rc) return rc;
       g_pool.info = g_pool.ctx[0]->info;
@@ -2198,10 +2233,12 @@ int swb200_score_batch_packed(const unsigned long long* q_words, long long q_str
     }
     g_pool.info_valid = false;
   }
+  const LenScan sc = scan_lens(q_len, t_len, 0, npairs, true);
+  if (!lens_ok(sc)) return fail(SWB200_ERR_ARG, lens_msg);
   swb200_ctx* c = nullptr;
   int rc = default_ctx(&c);
   if (rc) return rc;
-  return score_batch_packed_ctx(c, q_words, q_stride, t_words, t_stride, q_len, t_len, npairs, max_short, max_long, p, opt, scores_out);
+  return score_batch_packed_ctx(c, q_words, q_stride, t_words, t_stride, q_len, t_len, npairs, sc.max_q, sc.max_t, p, opt, scores_out, 0, 0, 0, sc.cells);
 }
 
 }  // extern "C"
