@@ -8,6 +8,6 @@ for flags in "$@"; do
   echo "=== flags: $flags"
   $NV $flags -c concurrentproject_b200/csrc/swb_chain.cu -o /tmp/swb_chain_var.o 2>/dev/null || { echo build failed; continue; }
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o concurrentproject_b200/lib/libswb200.so $OBJS /tmp/swb_chain_var.o -lpthread
-  timeout 200 python bench/chain_stress.py ${REPS:-60} 2>&1 | tail -4
+  timeout 200 python bench/chain_stress.py ${REPS:-30} 2>&1 | tail -4
 done
 cp /tmp/libswb200.keep concurrentproject_b200/lib/libswb200.so

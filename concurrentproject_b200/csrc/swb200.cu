@@ -591,7 +591,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
   const long long LQ1 = ts ? LQ - mid : 0, NB1 = ts ? (LQ1 + rpb - 1) / rpb : 0, pad1 = NB1 * rpb - LQ1;
 
   int per_sm = 0;
-  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, chain ? 160 : wpc * 32, 0));
+  SWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, chain ? swb::kChainThreads : wpc * 32, 0));
   if (per_sm < 1) return fail(SWB200_ERR_CUDA, "engine kernel does not fit on an SM");
   const long long want_warps = ts ? 2 * std::max(NB0, NB1) : NB;
   long long ctas = std::min<long long>((want_warps + wpc - 1) / wpc, (long long)c->sms);   // one CTA per SM
@@ -735,7 +735,7 @@ int run_once(swb200_ctx* c, const uint8_t* d_seq1, long long n, const uint8_t* d
       B2.links = c->d_chain + (size_t)chain_ctas0 * (size_t)chain_stride; B2.final_out = final_b;
     }
     void* cargs[] = {&CL};
-    SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3(160u), cargs, 0, s));
+    SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)swb::kChainThreads), cargs, 0, s));
   } else
   SWB_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3((unsigned)(wpc * 32)), args, 0, s));
   if (ts && ring) {

@@ -5,7 +5,7 @@
 // short-chain row loop); what changes is everything AROUND the step, which ncu's source page showed to be a third of the
 // sweep (profiles/r02_cfg2_base_stalls.json: per-chunk code 15 %, boundary waits 13 %):
 //
-//   * a CTA is four compute warps that own four CONSECUTIVE bands, plus one helper warp.  The bottom boundary row of
+//   * a CTA is four compute warps that own four CONSECUTIVE bands, plus one helper warp (two in the affine kernels).  The bottom boundary row of
 //     warp w goes straight into the shared-memory inbox of warp w+1: lane 31 keeps the values of a group of steps in
 //     registers and stores them after the group (predicated 16-byte stores, a CTA fence, then a step counter the
 //     consumer polls).  Three of four hand-offs never leave the SM.  Warp 3 (and the last band of a side) stores
@@ -13,7 +13,9 @@
 //   * the helper warp does what the compute warps' chunk prologue did: it expands the streamed sequence into the
 //     CTA's ring of 4-byte substitution tables (one ring for all four warps), polls the L2 link of the CTA above,
 //     validates the tagged entries and stages them in warp 0's inbox.  It shares a scheduler with one compute warp,
-//     fills issue slots that warp leaves empty and sleeps when it has nothing to do.
+//     fills issue slots that warp leaves empty and sleeps when it has nothing to do -- and still slows that warp by 2-3
+//     cycles per step, so WHICH warp it sits next to matters (the slowest band paces the chain): the CTA has eight warp
+//     slots, the helper(s) are picked among warps 4-7 per kernel flavour (see SWB_CHAIN_HELPER_WARP below), the rest exit.
 //   * what is left in a compute warp between two groups of 32 (linear, rows <= 3) or 16 steps: ONE conditional branch
 //     (the loop back-edge, on a counter and a back-pressure word read a few steps earlier), one predicated store of its
 //     own progress, two address computations.  A single warp per scheduler pays 20-30 cycles per branch.
@@ -46,6 +48,38 @@ SWB_HD constexpr int chain_group(int mode, int R) { return (mode == 1 && R <= 3)
 #endif
 constexpr int kChainInb = 512;       // entries of a compute warp's inbox ring
 constexpr int kChainTab = 2048;      // entries of the CTA's table ring (kept twice)
+// Helper warps.  A helper shares its scheduler with compute warp (its index % 4) and slows that warp's steps by the issue
+// slots it takes -- and the slowest band paces the whole chain (measured per warp on cfg2: 40.3 cycles per step next to the
+// helper, 37.5 elsewhere).  Warps 4-7 that are no helper exit at once.  Measured placements (profiles/r02_chain_experiments.txt):
+// linear-gap kernels: ONE helper as warp 7 -- it sits next to warp 3, whose global sink makes it the fastest of the four
+// (cfg2 3.106 -> 3.032 ms); affine kernels: the work split over TWO helpers on two schedulers (tables: warp 5; L2 link and
+// warp 0's counter: warp 6) that sleep 300 ns when idle (4.535 -> 4.436 ms).  Two helpers cost the linear kernel more in
+// polling than they spread.
+#ifndef SWB_CHAIN_HELPERS                      // helpers of the linear-gap kernels
+#define SWB_CHAIN_HELPERS 1
+#endif
+#ifndef SWB_CHAIN_HELPERS_AFF
+#define SWB_CHAIN_HELPERS_AFF 2
+#endif
+#ifndef SWB_CHAIN_HELPER_WARP                  // the boundary helper (with one helper: the only helper), linear / affine
+#define SWB_CHAIN_HELPER_WARP 7
+#endif
+#ifndef SWB_CHAIN_HELPER_WARP_AFF
+#define SWB_CHAIN_HELPER_WARP_AFF 6
+#endif
+#ifndef SWB_CHAIN_TABLE_WARP                   // the table helper (two helpers only)
+#define SWB_CHAIN_TABLE_WARP 5
+#endif
+#ifndef SWB_CHAIN_TABLE_WARP_AFF
+#define SWB_CHAIN_TABLE_WARP_AFF 5
+#endif
+#ifndef SWB_CHAIN_HELPER_SLEEP                 // ns an idle helper sleeps between two looks, linear / affine
+#define SWB_CHAIN_HELPER_SLEEP 100
+#endif
+#ifndef SWB_CHAIN_HELPER_SLEEP_AFF
+#define SWB_CHAIN_HELPER_SLEEP_AFF 300
+#endif
+constexpr int kChainThreads = 256;
 constexpr int kChainSK = 3;          // T positions between neighbouring lanes (two sub-lanes + the slack step)
 constexpr int kChainSkew = 31 * kChainSK + 1;
 
@@ -80,6 +114,7 @@ struct ChainSmem {
   int abort;
   uint32_t tagw;                          // P.tag, read back through shared memory so that it lives in a register (see chain_compute)
   int never;                              // 0x3fffffff: the back-pressure word of a warp whose sink is not a shared-memory inbox
+  int tab_pub;                            // two helpers: tables are ready up to this T position (table helper -> boundary helper)
 #ifdef SWB_CHAIN_CHECK
   // Protocol checker (bench/chain_variants.sh "-DSWB_CHAIN_CHECK"; compute-sanitizer is closed on this GPU pool): next to
   // every inbox slot the producer step it holds, next to every table slot its T position.  Every read of the step loop
@@ -155,6 +190,7 @@ static __device__ __noinline__ int chain_slow(const int* cnt_in, int need, const
 // ---------------------------------------------------------------------------------------------------------------
 //  helper warp
 // ---------------------------------------------------------------------------------------------------------------
+template <int ROLE, int SLEEP>   // ROLE 0: tables and boundary (the only helper), 1: tables, 2: boundary + warp 0's counter; SLEEP: ns when idle
 static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem* sm, int c, int lane, int nact) {
   const int LT = P.LT;
   const int nsteps = ((LT + kChainSkew + kChainGMax - 1) / kChainGMax) * kChainGMax;
@@ -166,17 +202,20 @@ static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem
   const uint32_t padw = padb * 0x01010101u;
   const uint32_t flip = padb ^ ((uint32_t)(P.match + P.gap_init) & 0xFFu);
   const uint64_t* tp = P.t_packed;
-  int tab_pos = 0;
-  int bnd_pos = has_src ? 0 : 0x3fffffff;
-  uint64_t tw = LT > 0 ? ld_early_u64(tp) : 0ull;                   // packed word of positions [tab_pos, tab_pos + 32)
+  int tab_pos = 0;                                                  // ROLE 2: what the table helper has published
+  int bnd_pos = (has_src && ROLE != 1) ? 0 : 0x3fffffff;
+  uint64_t tw = (ROLE != 2 && LT > 0) ? ld_early_u64(tp) : 0ull;     // packed word of positions [tab_pos, tab_pos + 32)
   long long budget = P.spin_limit;
   int idle = 0;
   while (tab_pos < tab_end || bnd_pos < LT) {
     bool progress = false;
     const int d0 = chain_ld(&sm->done[0]);
-    const int dl = chain_ld(&sm->done[nact - 1]);
+    if (ROLE == 2) {
+      const int tpub = chain_ld(&sm->tab_pub);
+      if (tpub != tab_pos) { tab_pos = tpub; progress = true; }
+    }
     // ---- substitution tables: at most 768 positions ahead of warp 0, never over entries the last warp still reads
-    if (tab_pos < tab_end && tab_pos + 32 <= dl - 128 + kChainTab && (tab_pos < d0 + 768 || bnd_pos >= LT)) {
+    if (ROLE != 2 && tab_pos < tab_end && tab_pos + 32 <= chain_ld(&sm->done[nact - 1]) - 128 + kChainTab && (tab_pos < d0 + 768 || (ROLE == 0 && bnd_pos >= LT))) {
       const int q = tab_pos + lane;
       uint32_t code = 4;
       if (q < LT) code = (uint32_t)(tw >> (2 * lane)) & 3u;
@@ -192,12 +231,15 @@ static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem
       progress = true;
     }
     // ---- boundary row of the CTA above: L2 link -> warp 0's inbox (positions beyond LT do not exist and count as present)
-    if (bnd_pos < LT && bnd_pos + 32 <= d0 + kChainInb - 64) {
+    if (ROLE != 1 && bnd_pos < LT && bnd_pos + 32 <= d0 + kChainInb - 64) {
       const int p = bnd_pos + lane;
       uint2 e = make_uint2(0u, tag);
       if (p < LT) e = ld_entry(lin + p + kChainSkew);
       const unsigned okm = __ballot_sync(0xffffffffu, e.y == tag);
-      const int n = okm == 0xffffffffu ? 32 : __ffs((int)~okm) - 1;
+      int n = okm == 0xffffffffu ? 32 : __ffs((int)~okm) - 1;
+#ifdef SWB_CHAIN_HELPER_MINFWD                                        // experiment: forward only batches of at least this many entries
+      if (n < SWB_CHAIN_HELPER_MINFWD && bnd_pos + n < LT) n = 0;
+#endif
       if (lane < n && p < LT) {
         const int slot = (p + kChainSkew) & (kChainInb - 1);
         sm->inbox[0][slot] = e.x;
@@ -212,14 +254,15 @@ static __device__ __noinline__ void chain_helper(const ChainParams& P, ChainSmem
     if (progress) {
       __syncwarp();
       __threadfence_block();
-      if (lane == 0) chain_st(&sm->cnt[0], ((bnd_pos >= LT || tab_pos < bnd_pos) ? tab_pos : bnd_pos) + kChainSkew);
+      if (ROLE == 1) { if (lane == 0) chain_st(&sm->tab_pub, tab_pos); }
+      else if (lane == 0) chain_st(&sm->cnt[0], ((bnd_pos >= LT || tab_pos < bnd_pos) ? tab_pos : bnd_pos) + kChainSkew);
       budget = P.spin_limit;
       idle = 0;
-    } else {
-#ifndef SWB_CHAIN_HELPER_SLEEP
-#define SWB_CHAIN_HELPER_SLEEP 100
+#ifdef SWB_CHAIN_HELPER_NAP                                           // experiment: rest after every piece of work as well
+      __nanosleep(SWB_CHAIN_HELPER_NAP);
 #endif
-      __nanosleep(SWB_CHAIN_HELPER_SLEEP);                          // an idle helper leaves the scheduler to the compute warp it shares it with
+    } else {
+      __nanosleep(SLEEP);                          // an idle helper leaves the scheduler to the compute warp it shares it with
       bool give_up = --budget < 0 || chain_ld(&sm->abort);
       if ((++idle & 255) == 0) give_up = give_up || (ld_flag(P.result + 1) & STATUS_SPIN_TIMEOUT);
       if (give_up) {
@@ -470,7 +513,7 @@ __device__ __forceinline__ void chain_compute(const ChainParams& P, ChainSmem* s
 }
 
 template <int R, int MODE>
-__global__ void __launch_bounds__(160, 1) sw_chain_kernel(const __grid_constant__ ChainLaunch L) {
+__global__ void __launch_bounds__(kChainThreads, 1) sw_chain_kernel(const __grid_constant__ ChainLaunch L) {
   __shared__ ChainSmem sm;
   const bool second = (int)blockIdx.x >= L.split;
   const ChainParams& P = second ? L.b : L.a;
@@ -493,11 +536,21 @@ __global__ void __launch_bounds__(160, 1) sw_chain_kernel(const __grid_constant_
     for (int i = (int)threadIdx.x; i < 2 * kChainTab; i += (int)blockDim.x) sm.tab_pos[i] = 0xffff;
 #endif
     if (threadIdx.x < 4) { sm.cnt[threadIdx.x] = 0; sm.done[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { sm.abort = 0; sm.tagw = P.tag; sm.never = 0x3fffffff; }
+    if (threadIdx.x == 0) { sm.abort = 0; sm.tagw = P.tag; sm.never = 0x3fffffff; sm.tab_pub = 0; }
   }
   __syncthreads();
-  if (wi == 4) chain_helper(P, &sm, c, lane, nact);
-  else if (wi < nact) chain_compute<R, MODE>(P, &sm, c, wi, lane, nact);
+  constexpr int HB = MODE == 1 ? SWB_CHAIN_HELPER_WARP : SWB_CHAIN_HELPER_WARP_AFF;
+  constexpr int HT = MODE == 1 ? SWB_CHAIN_TABLE_WARP : SWB_CHAIN_TABLE_WARP_AFF;
+  constexpr int NH = MODE == 1 ? SWB_CHAIN_HELPERS : SWB_CHAIN_HELPERS_AFF;
+  constexpr int SL = MODE == 1 ? SWB_CHAIN_HELPER_SLEEP : SWB_CHAIN_HELPER_SLEEP_AFF;
+  static_assert(HB >= 4 && HB < 8 && HT >= 4 && HT < 8 && (NH == 1 || HB != HT), "helper warps are warps 4-7");
+  if (NH == 1) {
+    if (wi == HB) chain_helper<0, SL>(P, &sm, c, lane, nact);
+  } else {
+    if (wi == HT) chain_helper<1, SL>(P, &sm, c, lane, nact);
+    if (wi == HB) chain_helper<2, SL>(P, &sm, c, lane, nact);
+  }
+  if (wi < nact) chain_compute<R, MODE>(P, &sm, c, wi, lane, nact);
 }
 
 #endif  // __CUDACC__
