@@ -67,3 +67,41 @@ def test_no_gpu_fails_loudly(lib):
     from concurrentproject_b200 import api
     with pytest.raises(api.SwbError):
         api.score(b"ACGT", b"ACGT")
+
+
+def test_host_packers_write_the_resident_format(lib):
+    """swb200_pack_batch_host / swb200_pack_banded_host are format conversion on the host (no GPU): symbol k of a sequence
+    lands at bits 2*(k%32) of word k/32 as (c >> 1) & 3; the batch packer puts the shorter sequence first, the banded
+    packer keeps seq1 / seq2; a byte outside A,C,G,T is an error."""
+    import numpy as np
+    from concurrentproject_b200 import api, rng
+
+    def decode(words, stride, k, n):
+        w = words[k * stride:(k + 1) * stride]
+        return np.array([(int(w[i >> 5]) >> (2 * (i & 31))) & 3 for i in range(n)], dtype=np.uint8)
+
+    r = np.random.default_rng(3)
+    s1 = [bytes(rng.random_acgt(3, k, int(r.integers(0, 200)))) for k in range(9)] + [b"", b"ACGT" * 16]
+    s2 = [bytes(rng.random_acgt(3, 100 + k, int(r.integers(0, 200)))) for k in range(9)] + [b"ACG", b""]
+    f1, o1, l1 = api._flatten(s1); f2, o2, l2 = api._flatten(s2)
+    code = lambda b: (np.frombuffer(b, dtype=np.uint8) >> 1) & 3
+
+    w1, st1, w2, st2 = api.pack_banded_host(f1, o1, l1, f2, o2, l2)
+    assert st1 == (max(map(len, s1)) + 31) // 32 + 2 and st2 == (max(map(len, s2)) + 31) // 32 + 2
+    for k, (a, b) in enumerate(zip(s1, s2)):
+        assert np.array_equal(decode(w1, st1, k, len(a)), code(a)) and np.array_equal(decode(w2, st2, k, len(b)), code(b))
+        assert not w1[k * st1 + (len(a) + 31) // 32:(k + 1) * st1].any()          # words beyond the end are zero
+
+    qw, qs, tw, ts, ql, tl = api.pack_batch_host(f1, o1, l1, f2, o2, l2)
+    for k, (a, b) in enumerate(zip(s1, s2)):
+        short, long_ = (a, b) if len(a) <= len(b) else (b, a)
+        assert (ql[k], tl[k]) == (len(short), len(long_))
+        assert np.array_equal(decode(qw, qs, k, len(short)), code(short)) and np.array_equal(decode(tw, ts, k, len(long_)), code(long_))
+
+    bad = np.frombuffer(b"ACGN", dtype=np.uint8)
+    ok = np.frombuffer(b"ACGT", dtype=np.uint8)
+    z, four = np.zeros(1, np.int64), np.array([4], np.int32)
+    with pytest.raises(api.SwbError):
+        api.pack_banded_host(ok, z, four, bad, z, four)
+    with pytest.raises(api.SwbError):
+        api.pack_batch_host(bad, z, four, ok, z, four)
