@@ -83,6 +83,16 @@ def test_set_devices_from_python():
             assert api.score(a, b) == O.gotoh_rolling(a, b)
             assert api.score(a, b, (2, -3, 5, 1)) == O.gotoh_rolling(a, b, (2, -3, 5, 1))
             assert api.last_run()["warps"] >= 8
+            # host batches in the 2-bit format, sharded over the two devices (each shard's lengths scanned by its own thread)
+            r = np.random.default_rng(5)
+            s1 = [bytes(rng.random_acgt(34, k, int(r.integers(0, 150)))) for k in range(301)]
+            s2 = [bytes(rng.mutate(np.frombuffer(x, np.uint8), 34, 400 + k, 0.06, 0.02)) if k % 2 and len(x) else
+                  bytes(rng.random_acgt(34, 800 + k, int(r.integers(0, 700)))) for k, x in enumerate(s1)]
+            f1, o1, l1 = api._flatten(s1); f2, o2, l2 = api._flatten(s2)
+            qw, qs, tw, ts, ql, tl = api.pack_batch_host(f1, o1, l1, f2, o2, l2)
+            assert np.array_equal(api.score_batch_packed(qw, qs, tw, ts, ql, tl), O.gotoh_batch(s1, s2))
+            w1, st1, w2, st2 = api.pack_banded_host(f1, o1, l1, f2, o2, l2)
+            assert np.array_equal(api.score_banded_batch_packed(w1, st1, w2, st2, l1, l2, -20, 43), O.gotoh_banded_batch(s1, s2, -20, 43))
         finally:
             api.set_devices(1)
             api.configure("ring_min_cells", str(200 * 10**9))
