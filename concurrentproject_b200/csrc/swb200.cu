@@ -467,9 +467,10 @@ double estimate_chain(long long LQ, long long LT, int mode, int R, int sms, bool
   if ((NB0 + 3) / 4 + (NB1 + 3) / 4 > sms) return 1e300;
   // fitted on one-sided sweeps of a 100 000-row Q against T of 25 000 ... 400 000 (bench/chain_fit.py, profiles/r02_chain_fit.txt):
   // groups of 32 steps: 44.0 cycles per step at R = 3 linear, a band starts 150 steps after the band above it;
-  // groups of 16 steps: 67.9 cycles per step at R = 3 affine, 125 steps
+  // groups of 16 steps: 67.9 cycles per step at R = 3 affine, 125 steps.  With the helper warps placed as they are now
+  // (swb_chain.cuh, SWB_CHAIN_HELPER_WARP): 42.8 and 65.7 on cfg2.
   const bool g32 = swb::chain_group(mode, R) == 32;
-  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + (g32 ? 23.0 : 28.0);
+  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + (g32 ? 21.8 : 26.1);
   const double lag = g32 ? 150.0 : 125.0;
   const double bands = (double)std::max(NB0, NB1);
   return ((bands - 1.0) * lag + (double)(LT + swb::kChainSkew)) * cyc_step + (two_sided ? 30000.0 : 0.0);
