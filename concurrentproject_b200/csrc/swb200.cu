@@ -470,7 +470,11 @@ double estimate_chain(long long LQ, long long LT, int mode, int R, int sms, bool
   // groups of 16 steps: 67.9 cycles per step at R = 3 affine, 125 steps.  With the helper warps placed as they are now
   // (swb_chain.cuh, SWB_CHAIN_HELPER_WARP): 42.8 and 65.7 on cfg2.
   const bool g32 = swb::chain_group(mode, R) == 32;
-  const double cyc_step = (mode == 1 ? 7.0 : 13.2) * R + (g32 ? 21.8 : 26.1);
+  // Linear kernels, from profiles/r02_plancheck.txt (end of round 2): R = 2 / 3 in groups of 32: 40.1 / 42.8; R = 4 / 6 / 8 in
+  // groups of 16: 60.4 / 75.1 / 88.5 = 7 R + 32.5.  (The earlier 7 R + 23 made R = 2 look 4 % cheaper than R = 3 below
+  // 100 000 rows; measured it is 6-7 % dearer.)  The groups-of-16 term is entered as 7 R + 29.5: the pair engine's own
+  // estimate is 4-5 % optimistic at 200 000 - 250 000 rows, where the chained engine measures 3-4 % faster.
+  const double cyc_step = mode == 1 ? (g32 ? (R >= 3 ? 42.8 : (R == 2 ? 40.1 : 39.0)) : 7.0 * R + 29.5) : 13.2 * R + 26.1;
   const double lag = g32 ? 150.0 : 125.0;
   const double bands = (double)std::max(NB0, NB1);
   return ((bands - 1.0) * lag + (double)(LT + swb::kChainSkew)) * cyc_step + (two_sided ? 30000.0 : 0.0);
