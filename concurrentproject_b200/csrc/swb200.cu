@@ -2106,34 +2106,82 @@ int swb200_batch_strides(int max_short, int max_long, long long* q_stride, long 
 
 // Format conversion on the host (no scoring here): raw A,C,G,T bytes -> the resident 2-bit layout, shorter sequence of
 // each pair first.  Same words as the device packer (swb_batch.cu: pack_batch_kernel) produces.
-static int pack_host_impl(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
-                          const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
-                          unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len, bool keep_order) {
-  if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !q_words || !t_words || !q_len || !t_len)))
-    return fail(SWB200_ERR_ARG, "bad batch arguments");
-  for (long long k = 0; k < npairs; ++k) {
+// 2-bit code of a byte, 0xFF for anything but A,C,G,T (the codes of the device packer: (c >> 1) & 3)
+struct PackLut {
+  unsigned char v[256];
+  PackLut() { memset(v, 0xFF, sizeof v); v['A'] = 0; v['C'] = 1; v['G'] = 3; v['T'] = 2; }
+};
+static const PackLut g_pack_lut;
+
+// pairs [k0, k1): 0 = fine, 1 = a pair does not fit the strides, 2 = a byte other than A,C,G,T
+static int pack_host_range(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                           const long long* off2, const int* len2, long long k0, long long k1, long long q_stride, long long t_stride,
+                           unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len, bool keep_order) {
+  const unsigned char* const lut = g_pack_lut.v;
+  unsigned bad = 0;
+  for (long long k = k0; k < k1; ++k) {
     const bool swap = !keep_order && len1[k] > len2[k];
     const unsigned char* q = swap ? seq2_all + off2[k] : seq1_all + off1[k];
     const unsigned char* t = swap ? seq1_all + off1[k] : seq2_all + off2[k];
     const int lq = swap ? len2[k] : len1[k], lt = swap ? len1[k] : len2[k];
-    if (lq < 0 || lt < 0 || (lq + 31) / 32 + (keep_order ? 2 : 0) > q_stride || (lt + 31) / 32 + 2 > t_stride)
-      return fail(SWB200_ERR_ARG, "pair longer than the strides allow");
+    if (lq < 0 || lt < 0 || (lq + 31) / 32 + (keep_order ? 2 : 0) > q_stride || (lt + 31) / 32 + 2 > t_stride) return 1;
     for (int side = 0; side < 2; ++side) {
       const unsigned char* src = side ? t : q;
       const int len = side ? lt : lq;
       unsigned long long* dst = side ? t_words + k * t_stride : q_words + k * q_stride;
       const long long stride = side ? t_stride : q_stride;
-      for (long long w = 0; w < stride; ++w) {
+      const long long full = len / 32;
+      for (long long w = 0; w < full; ++w) {                       // whole words: 32 table look-ups, no bounds test
+        const unsigned char* s32 = src + w * 32;
+        unsigned long long out = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const unsigned v = lut[s32[b]];
+          bad |= v;
+          out |= (unsigned long long)(v & 3u) << (2 * b);
+        }
+        dst[w] = out;
+      }
+      for (long long w = full; w < stride; ++w) {
         unsigned long long out = 0;
         for (int b = 0; b < 32 && w * 32 + b < len; ++b) {
-          const unsigned c = src[w * 32 + b], v = (c >> 1) & 3u;
-          if (c != ((0x47544341u >> (8 * v)) & 0xFFu)) return fail(SWB200_ERR_ALPHABET, "batch input contains bytes other than A,C,G,T");
-          out |= (unsigned long long)v << (2 * b);
+          const unsigned v = lut[src[w * 32 + b]];
+          bad |= v;
+          out |= (unsigned long long)(v & 3u) << (2 * b);
         }
         dst[w] = out;
       }
     }
     q_len[k] = lq; t_len[k] = lt;
+  }
+  return (bad & 0x80u) ? 2 : 0;
+}
+
+// Format conversion on the host, spread over up to 16 threads (5 GB of long reads are seconds of work for one).
+static int pack_host_impl(const unsigned char* seq1_all, const long long* off1, const int* len1, const unsigned char* seq2_all,
+                          const long long* off2, const int* len2, long long npairs, long long q_stride, long long t_stride,
+                          unsigned long long* q_words, unsigned long long* t_words, int* q_len, int* t_len, bool keep_order) {
+  if (npairs < 0 || (npairs > 0 && (!seq1_all || !seq2_all || !off1 || !off2 || !len1 || !len2 || !q_words || !t_words || !q_len || !t_len)))
+    return fail(SWB200_ERR_ARG, "bad batch arguments");
+  long long bytes = 0;
+  for (long long k = 0; k < npairs; ++k) bytes += (long long)(len1[k] > 0 ? len1[k] : 0) + (len2[k] > 0 ? len2[k] : 0);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int T = (int)std::max<long long>(1, std::min<long long>({16LL, (long long)hw, bytes >> 22, npairs}));   // >= 4 MB per thread
+  std::vector<int> rc((size_t)T, 0);
+  auto run = [&](int t) {
+    const long long k0 = npairs * t / T, k1 = npairs * (t + 1) / T;
+    rc[(size_t)t] = pack_host_range(seq1_all, off1, len1, seq2_all, off2, len2, k0, k1, q_stride, t_stride, q_words, t_words, q_len, t_len, keep_order);
+  };
+  if (T == 1) run(0);
+  else {
+    std::vector<std::thread> th;
+    th.reserve((size_t)T);
+    for (int t = 0; t < T; ++t) th.emplace_back(run, t);
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < T; ++t) {
+    if (rc[(size_t)t] == 1) return fail(SWB200_ERR_ARG, "pair longer than the strides allow");
+    if (rc[(size_t)t] == 2) return fail(SWB200_ERR_ALPHABET, "batch input contains bytes other than A,C,G,T");
   }
   return SWB200_OK;
 }
