@@ -105,3 +105,27 @@ def test_host_packers_write_the_resident_format(lib):
         api.pack_banded_host(ok, z, four, bad, z, four)
     with pytest.raises(api.SwbError):
         api.pack_batch_host(bad, z, four, ok, z, four)
+
+
+def test_packed_batch_calls_validate_their_arguments_before_touching_a_gpu(lib):
+    """Lengths that break the packed layout are refused by the branch-free length scan, on any machine: a q longer than its
+    t, a negative length, a pair longer than the strides allow; the banded call also wants strides of at least 3 words."""
+    import numpy as np
+    from concurrentproject_b200 import api
+    qs, ts = api.batch_strides(40, 90)
+    qw, tw = np.zeros(3 * qs, dtype=np.uint64), np.zeros(3 * ts, dtype=np.uint64)
+    i32 = lambda *v: np.array(v, dtype=np.int32)
+    for ql, tl in ((i32(10, 50, 10), i32(20, 40, 30)),            # q longer than t
+                   (i32(10, -1, 10), i32(20, 40, 30)),            # negative
+                   (i32(10, 20, 41 + 32), i32(20, 40, 90)),       # q beyond its stride
+                   (i32(10, 20, 30), i32(20, 40, 90 + 64))):      # t beyond its stride
+        with pytest.raises(api.SwbError) as e:
+            api.score_batch_packed(qw, qs, tw, ts, ql, tl)
+        assert e.value.code == -2, (ql, tl)                         # SWB200_ERR_ARG
+    w = np.zeros(12, dtype=np.uint64)
+    with pytest.raises(api.SwbError) as e:
+        api.score_banded_batch_packed(w, 2, w, 4, i32(10, 10, 10), i32(10, 10, 10))
+    assert e.value.code == -2
+    with pytest.raises(api.SwbError) as e:
+        api.score_banded_batch_packed(w, 4, w, 4, i32(10, 70, 10), i32(10, 10, 10))      # 70 symbols need 3 + 2 words
+    assert e.value.code == -2
