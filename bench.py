@@ -603,7 +603,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=ALL_WORKLOADS)
     ap.add_argument("--no-extra", action="store_true", help="headline only: skip the cfg3 ring and cfg4 batch sub-records")
     ap.add_argument("--lanes32", action="store_true", help="ring workloads: force the 32-bit kernel")
-    ap.add_argument("--banded-config", type=int, default=0, help="banded workloads: 16 = the 16-threads-per-pair kernel layout")
+    ap.add_argument("--banded-config", type=int, default=0, help="banded workloads: 0 = 4 threads per pair (default), 2 / 8 / 16 = the other kernel layouts")
     ap.add_argument("--one-sided", action="store_true", help="ring workloads: never sweep from both ends")
     ap.add_argument("--no-linear", action="store_true",
                     help="keep the general affine kernel although GAP_INIT == GAP_EXT (default: use the exact E/F-free kernel)")

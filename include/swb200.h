@@ -46,7 +46,7 @@ typedef struct {
                       7 = the CTA-chained engine (csrc/swb_chain.cuh: one band per warp, four consecutive bands per CTA handed
                       over through shared memory; plain 16-bit lanes, one GPU, rows 1,2,3,4,6,8) -- what "auto" picks for
                       fill-dominated pairs such as 100 000 x 100 000.
-                      banded calls: 0 = 4 threads per pair (default), 8 = 8 threads per pair, 16 = 16 threads per pair */
+                      banded calls: 0 = 4 threads per pair (default), 8 = 8 threads per pair, 16 = 16 threads per pair, 2 = 2 threads per pair */
   int ctas;        /* thread blocks (<= co-resident limit); 0 auto */
   int no_linear;   /* 1 = keep the affine kernel even when gap_init == gap_ext */
   int orient;      /* 0 auto (stripe the longer sequence across lanes), 1 = stripe seq1, 2 = stripe seq2 */
