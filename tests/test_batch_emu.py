@@ -70,3 +70,8 @@ def test_banded_kernel_body(emu, G):
         for p, mode in ((O.DEFAULT, 1), (O.DEFAULT, 0), ((2, -3, 5, 1), 0), ((3, -2, 3, 1), 0), ((3, -2, 2, 2), 1)):
             want = O.gotoh_banded_batch(a, b, lo, lo + 63, p).tolist()
             assert emu(a, b, "banded", 0, mode, G, p, band_lo=lo) == want, (lo, p, mode, G)
+    if G == 4:      # the default layout refills its rings from rolling 64-bit windows whose bit offset follows band_lo: more offsets
+        for lo in (-33, -31, -1, 30, -64, -63, 11, -47):
+            for p, mode in ((O.DEFAULT, 1), ((2, -3, 5, 1), 0)):
+                want = O.gotoh_banded_batch(a, b, lo, lo + 63, p).tolist()
+                assert emu(a, b, "banded", 0, mode, G, p, band_lo=lo) == want, (lo, p, mode, G)
