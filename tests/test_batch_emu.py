@@ -71,7 +71,7 @@ def test_banded_kernel_body(emu, G):
             want = O.gotoh_banded_batch(a, b, lo, lo + 63, p).tolist()
             assert emu(a, b, "banded", 0, mode, G, p, band_lo=lo) == want, (lo, p, mode, G)
     if G == 4:      # the default layout refills its rings from rolling 64-bit windows whose bit offset follows band_lo: more offsets
-        for lo in (-33, -31, -1, 30, -64, -63, 11, -47):
+        for lo in (-33, -1, -63, 11):
             for p, mode in ((O.DEFAULT, 1), ((2, -3, 5, 1), 0)):
                 want = O.gotoh_banded_batch(a, b, lo, lo + 63, p).tolist()
                 assert emu(a, b, "banded", 0, mode, G, p, band_lo=lo) == want, (lo, p, mode, G)
